@@ -1,0 +1,148 @@
+/*
+ * mfs_b200.h -- C ABI of the B200-native batched moment filter (drop-in for the hot path of zgbkdlm/mfs).
+ *
+ * The reference has no native boundary: its "operator API" is the Python signature of
+ *   moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, stable)      mfs/one_dim/filtering.py:32-36
+ *   moment_filter_cms(state_cond_central_moments, state_cond_mean, pdf, cms0, mean0, ys)   mfs/one_dim/filtering.py:92-98
+ *   moment_filter_scms(... scms0, mean0, scale0, ys)                                       mfs/one_dim/filtering.py:164-172
+ *   moment_quadrature(ms, mean, scale, sort_nodes, ldl)                                    mfs/one_dim/quadtures.py:83-85
+ * taking Python callables.  Here the callables become *named device functors* (ids below) with packed double
+ * parameters, and one call runs B independent filters (the batch axis the reference fans out over OS processes,
+ * dardel/run_benes_bernoulli_mf.sh:26-45).  INTEGRATION.md shows the ctypes / XLA-FFI binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures: device pointers are `void*`/`double*`, the stream is `void*`
+ *     (a cudaStream_t; NULL = legacy default stream).
+ *   - the caller owns every buffer; `mfs_filter_1d` never allocates.  `mfs_filter_1d_host` (host buffers) owns a
+ *     per-call device workspace that it allocates and frees itself.
+ *   - return value 0 = launched/completed; negative = argument / CUDA error, text via mfs_last_error()
+ *     (thread-local).  NUMERICAL failure is not an error: like the JAX scan it yields NaN from the failing step
+ *     onwards, and status_out[b] = index of the first failed step (-1: none).
+ *   - all strides are in ELEMENTS of the pointed-to type.  A stride of 0 on a per-filter input means "shared by all
+ *     filters".
+ */
+#ifndef MFS_B200_H_
+#define MFS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFS_ABI_VERSION 1
+#define MFS_MAX_N 15          /* quadrature nodes; 2N moments.  Reference sweeps N=2..15 (dardel/run_time_profile.sh:25) */
+#define MFS_MAX_PARAMS 4
+
+/* moment representation: mfs/definitions.py (rms / cms / scms) */
+enum { MFS_MODE_RAW = 0, MFS_MODE_CENTRAL = 1, MFS_MODE_SCALED = 2 };
+
+/* transition-moment family: the three factories of mfs/one_dim/moments.py */
+enum {
+  MFS_TRANS_TME = 0,        /* sde_cond_moments_tme          moments.py:141-179  (order 1..3)              */
+  MFS_TRANS_TME_NORMAL = 1, /* sde_cond_moments_tme_normal   moments.py:182-219  N(mean,var) from TME      */
+  MFS_TRANS_EULER = 2,      /* sde_cond_moments_euler        moments.py:222-255  N(x+a dt, b^2 dt)         */
+  MFS_TRANS_NORMAL_AFFINE = 3 /* N(F x, Sigma): exact OU closure, dardel/convergence/convergence_mf.py:86-107;
+                                 trans_params = {F, Sigma} */
+};
+
+/* drift a(x) of dX = a(X) dt + b dW, constant dispersion b */
+enum {
+  MFS_DRIFT_BENES = 0,  /* tanh(x)                 mfs/one_dim/ss_models.py:37   params: -            */
+  MFS_DRIFT_WELL = 1,   /* x (1 - theta1 x^2)      mfs/one_dim/ss_models.py:71   params: {theta1}     */
+  MFS_DRIFT_LINEAR = 2  /* a x  (OU: a = -1/ell)   tests/test_filtering.py:45    params: {a}          */
+};
+
+/* measurement model p(y | x) */
+enum {
+  MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC = 0, /* Bernoulli(1/(1+exp(-(x^3/c0 - c1)))); Benes: {5,0} ss_models.py:43-47 */
+  MFS_MEAS_POISSON_SOFTPLUS = 1,         /* Poisson(log(1+exp(theta2 x)))   params {theta2}   ss_models.py:80-84  */
+  MFS_MEAS_GAUSSIAN = 2                  /* N(y; h x, r^2)   params {h, r}    tests/test_filtering.py:41-42       */
+};
+
+enum { MFS_YS_U8 = 0, MFS_YS_I32 = 1, MFS_YS_F64 = 2 };
+
+/* what the kernel writes back */
+enum {
+  MFS_OUT_FULL = 0, /* every step: ms_out[b][t][0..2N) (+ mean_out[b][t], scale_out[b][t]) like the reference */
+  MFS_OUT_LAST = 1, /* only the final step's moments (ms_out[b][0..2N)), mean, scale                          */
+  MFS_OUT_NONE = 2  /* only nell (parameter-estimation objective, dardel/parameter_estimation/mf.py:52)       */
+};
+
+typedef struct mfs_filter1d_args {
+  int32_t abi_version;   /* MFS_ABI_VERSION */
+  int32_t mode;          /* MFS_MODE_*  */
+  int32_t N;             /* 2..MFS_MAX_N */
+  int32_t stable;        /* 0/1: `stable=True` LDL completion (mfs/utils.py:526-538) */
+  int64_t B;             /* independent filters */
+  int64_t T;             /* time steps */
+
+  int32_t trans_id;      /* MFS_TRANS_* */
+  int32_t drift_id;      /* MFS_DRIFT_* (ignored by NORMAL_AFFINE) */
+  int32_t tme_order;     /* 1..3 for TME / TME_NORMAL */
+  int32_t meas_id;       /* MFS_MEAS_* */
+  double dt;
+  double dispersion;     /* constant b */
+  const double* trans_params; /* device, [B or 1][MFS_MAX_PARAMS] */
+  int64_t trans_param_stride; /* elements between filters; 0 = shared */
+  const double* meas_params;  /* device, [B or 1][MFS_MAX_PARAMS] */
+  int64_t meas_param_stride;
+
+  const double* ms0;     /* device, initial moments [B or 1][2N] */
+  int64_t ms0_stride;
+  const double* mean0;   /* CENTRAL/SCALED: [B or 1] */
+  int64_t mean0_stride;
+  const double* scale0;  /* SCALED: [B or 1] */
+  int64_t scale0_stride;
+
+  const void* ys;        /* device, measurement y[b][t] at ys + b*ys_stride_b + t*ys_stride_t */
+  int32_t ys_dtype;      /* MFS_YS_* */
+  int32_t out_mode;      /* MFS_OUT_* */
+  int64_t ys_stride_b;
+  int64_t ys_stride_t;
+
+  double* ms_out;        /* FULL: [B][T][2N] via strides below; LAST: [B][2N] (ms_stride_t ignored) */
+  int64_t ms_stride_b;
+  int64_t ms_stride_t;
+  double* mean_out;      /* FULL: [B][T] (stride_b = aux_stride_b, stride_t = 1); LAST: [B]; may be NULL in RAW mode */
+  double* scale_out;     /* same shape as mean_out; SCALED mode only */
+  int64_t aux_stride_b;
+  double* nell_out;      /* [B] negative log-likelihood */
+  int32_t* status_out;   /* [B] first failed step or -1; may be NULL */
+} mfs_filter1d_args;
+
+/* ABI version of the loaded library. */
+int mfs_abi_version(void);
+
+/* Last error text of the calling thread ("" if none). */
+const char* mfs_last_error(void);
+
+/* Look up a functor id by name, e.g. kind="drift", name="benes" -> MFS_DRIFT_BENES.  Kinds: "mode", "trans",
+ * "drift", "meas".  Returns 0 and writes *id, or -1 for an unknown name. */
+int mfs_functor_lookup(const char* kind, const char* name, int32_t* id);
+
+/* Enqueue B filters x T steps on `stream`; every pointer in `a` is a DEVICE pointer.  Asynchronous w.r.t. the host.
+ * Replaces: jax.jit(moment_filter_{rms,cms,scms})(ys) per trajectory (dardel/benes_bernoulli/mf.py:51-67). */
+int mfs_filter_1d(const mfs_filter1d_args* a, void* stream);
+
+/* Same contract with HOST pointers everywhere (ys, ms0, params, outputs).  The batch is cut into chunks that are
+ * pipelined H2D -> kernel -> D2H on `device` (double-buffered, two streams); returns after the last D2H completed.
+ * `chunk_filters` = 0 picks a default. */
+int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_filters);
+
+/* Batched moment quadrature (mfs/one_dim/quadtures.py:83-133): ms[B][2N] -> weights[B][N], nodes[B][N] (ascending
+ * nodes when sort_nodes != 0).  mean/scale may be NULL (0 / 1).  Device pointers. */
+int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
+                             int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream);
+
+/* Number of kernel launches issued by this library in the calling process since load (all threads). */
+int64_t mfs_launch_count(void);
+
+/* FP64 FMA throughput micro-benchmark used for the roofline denominator: runs `iters` dependent-chain-free DFMA
+ * blocks on the whole device and returns achieved FLOP/s (2 flop per FMA) in *flops.  Device pointers none. */
+int mfs_fp64_peak(int device, int32_t iters, double* flops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFS_B200_H_ */

@@ -1,0 +1,117 @@
+"""ctypes binding of ``libmfs_b200.so`` (C ABI in ``include/mfs_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded every entry point raises.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmfs_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+ABI_VERSION = 1
+MAX_N = 15
+MAX_PARAMS = 4
+
+MODE = {'raw': 0, 'central': 1, 'scaled': 2}
+TRANS = {'tme': 0, 'tme_normal': 1, 'euler': 2, 'normal_affine': 3}
+DRIFT = {'benes': 0, 'well': 1, 'linear': 2}
+MEAS = {'bernoulli_logistic_cubic': 0, 'poisson_softplus': 1, 'gaussian': 2}
+YS_DTYPE = {'uint8': 0, 'bool': 0, 'int32': 1, 'float64': 2}
+OUT_MODE = {'full': 0, 'last': 1, 'none': 2}
+
+
+class Filter1dArgs(ctypes.Structure):
+    """Mirror of ``mfs_filter1d_args``."""
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('mode', ctypes.c_int32), ('N', ctypes.c_int32), ('stable', ctypes.c_int32),
+        ('B', ctypes.c_int64), ('T', ctypes.c_int64),
+        ('trans_id', ctypes.c_int32), ('drift_id', ctypes.c_int32), ('tme_order', ctypes.c_int32),
+        ('meas_id', ctypes.c_int32),
+        ('dt', ctypes.c_double), ('dispersion', ctypes.c_double),
+        ('trans_params', ctypes.c_void_p), ('trans_param_stride', ctypes.c_int64),
+        ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
+        ('ms0', ctypes.c_void_p), ('ms0_stride', ctypes.c_int64),
+        ('mean0', ctypes.c_void_p), ('mean0_stride', ctypes.c_int64),
+        ('scale0', ctypes.c_void_p), ('scale0_stride', ctypes.c_int64),
+        ('ys', ctypes.c_void_p), ('ys_dtype', ctypes.c_int32), ('out_mode', ctypes.c_int32),
+        ('ys_stride_b', ctypes.c_int64), ('ys_stride_t', ctypes.c_int64),
+        ('ms_out', ctypes.c_void_p), ('ms_stride_b', ctypes.c_int64), ('ms_stride_t', ctypes.c_int64),
+        ('mean_out', ctypes.c_void_p), ('scale_out', ctypes.c_void_p), ('aux_stride_b', ctypes.c_int64),
+        ('nell_out', ctypes.c_void_p), ('status_out', ctypes.c_void_p),
+    ]
+
+
+EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
+           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak')
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MfsError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False, jobs: int = None) -> str:
+    """Compile the CUDA sources for sm_100a into ``mfs_b200/libmfs_b200.so`` (nvcc cross-compiles without a GPU)."""
+    jobs = jobs or max(1, os.cpu_count() or 1)
+    proc = subprocess.run(['make', '-C', CSRC, f'-j{jobs}'], capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout[-4000:])
+        print(proc.stderr[-8000:])
+    if proc.returncode != 0:
+        raise MfsError('building libmfs_b200.so failed (see output above)')
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises ``MfsError`` when it is absent -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MfsError(f'{LIB_PATH} not found: run `python -c "import __graft_entry__ as g; g.build()"` '
+                           f'(or `make -C mfs_b200/csrc -j`). There is no CPU fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        L.mfs_abi_version.restype = ctypes.c_int
+        L.mfs_last_error.restype = ctypes.c_char_p
+        L.mfs_functor_lookup.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int32)]
+        L.mfs_functor_lookup.restype = ctypes.c_int
+        L.mfs_filter_1d.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_void_p]
+        L.mfs_filter_1d.restype = ctypes.c_int
+        L.mfs_filter_1d_host.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_int, ctypes.c_int64]
+        L.mfs_filter_1d_host.restype = ctypes.c_int
+        L.mfs_moment_quadrature_1d.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p]
+        L.mfs_moment_quadrature_1d.restype = ctypes.c_int
+        L.mfs_launch_count.restype = ctypes.c_int64
+        L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]
+        L.mfs_fp64_peak.restype = ctypes.c_int
+        if L.mfs_abi_version() != ABI_VERSION:
+            raise MfsError(f'ABI mismatch: library {L.mfs_abi_version()} vs binding {ABI_VERSION}')
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MfsError(lib().mfs_last_error().decode() or f'libmfs_b200 returned {rc}')
+
+
+def launch_count() -> int:
+    return int(lib().mfs_launch_count())
+
+
+def fp64_peak(device: int = 0, iters: int = 4096):
+    """Measured FP64 FMA throughput (FLOP/s) of ``device``; the roofline denominator of the filter kernels."""
+    flops, ms = ctypes.c_double(), ctypes.c_double()
+    check(lib().mfs_fp64_peak(device, iters, ctypes.byref(flops), ctypes.byref(ms)))
+    return flops.value, ms.value

@@ -1,0 +1,360 @@
+// C ABI of libmfs_b200.so (declared in include/mfs_b200.h): validation, dispatch, host-buffer pipeline.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "filter1d.cuh"
+
+namespace mfs {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+
+#define MFS_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e__));    \
+  } while (0)
+
+static int ys_elem_size(int dtype) { return dtype == MFS_YS_U8 ? 1 : dtype == MFS_YS_I32 ? 4 : 8; }
+
+// Argument checks shared by the device and host entry points (pointer NULL-ness only; both address spaces).
+static int validate(const mfs_filter1d_args* a) {
+  if (!a) return fail("args is NULL");
+  if (a->abi_version != MFS_ABI_VERSION) return fail("abi_version %d != %d", a->abi_version, MFS_ABI_VERSION);
+  if (a->N < 2 || a->N > MFS_MAX_N) return fail("N=%d outside [2, %d]", a->N, MFS_MAX_N);
+  if (a->mode < MFS_MODE_RAW || a->mode > MFS_MODE_SCALED) return fail("unknown mode %d", a->mode);
+  if (a->B < 0 || a->T < 0) return fail("negative B or T");
+  if (a->trans_id < MFS_TRANS_TME || a->trans_id > MFS_TRANS_NORMAL_AFFINE) return fail("unknown trans_id %d", a->trans_id);
+  if (a->trans_id != MFS_TRANS_NORMAL_AFFINE && (a->drift_id < MFS_DRIFT_BENES || a->drift_id > MFS_DRIFT_LINEAR))
+    return fail("unknown drift_id %d", a->drift_id);
+  if ((a->trans_id == MFS_TRANS_TME || a->trans_id == MFS_TRANS_TME_NORMAL) && (a->tme_order < 1 || a->tme_order > 3))
+    return fail("tme_order=%d outside [1, 3]", a->tme_order);
+  if (a->meas_id < MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC || a->meas_id > MFS_MEAS_GAUSSIAN) return fail("unknown meas_id %d", a->meas_id);
+  if (a->ys_dtype < MFS_YS_U8 || a->ys_dtype > MFS_YS_F64) return fail("unknown ys_dtype %d", a->ys_dtype);
+  if (a->out_mode < MFS_OUT_FULL || a->out_mode > MFS_OUT_NONE) return fail("unknown out_mode %d", a->out_mode);
+  if (a->mode == MFS_MODE_SCALED && a->trans_id != MFS_TRANS_TME)
+    return fail("scaled central moments are only offered with the TME family: the reference's scaled Normal/Euler "
+                "factories divide every order by prod(scale**k) (mfs/one_dim/moments.py:205,243)");
+  if (a->stable) return fail("stable=True (LDL completion, mfs/utils.py:526-538) is not implemented in this build");
+  if (!(a->dt > 0.0)) return fail("dt must be > 0");
+  if (a->B == 0) return 0;
+  if (!a->ms0 || !a->trans_params || !a->meas_params || !a->nell_out) return fail("ms0 / trans_params / meas_params / nell_out must not be NULL");
+  if (a->T > 0 && !a->ys) return fail("ys is NULL");
+  if (a->mode != MFS_MODE_RAW && !a->mean0) return fail("mean0 is NULL in central/scaled mode");
+  if (a->mode == MFS_MODE_SCALED && !a->scale0) return fail("scale0 is NULL in scaled mode");
+  if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
+  if (a->out_mode != MFS_OUT_NONE && a->mode != MFS_MODE_RAW && !a->mean_out) return fail("mean_out is NULL in central/scaled mode");
+  if (a->out_mode != MFS_OUT_NONE && a->mode == MFS_MODE_SCALED && !a->scale_out) return fail("scale_out is NULL in scaled mode");
+  return 0;
+}
+
+static int pick_kind(const mfs_filter1d_args& a) {
+  if (a.trans_id == MFS_TRANS_TME) {
+    if (a.drift_id == MFS_DRIFT_BENES && a.dispersion == 1.0) return KIND_BENES_TME;
+    return KIND_TME;
+  }
+  return KIND_NORMAL;
+}
+
+static cudaError_t dispatch(const mfs_filter1d_args& a, cudaStream_t s) {
+  const int kind = pick_kind(a);
+  switch (a.N) {
+#define MFS_CASE(n) case n: return launch_filter1d<n>(a, kind, s);
+    MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
+    MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
+#undef MFS_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
+  if (a.B == 0) return 0;
+  if (a.out_mode != MFS_OUT_NONE) {
+    if ((reinterpret_cast<uintptr_t>(a.ms_out) & 15) || (a.ms_stride_b & 1) ||
+        (a.out_mode == MFS_OUT_FULL && (a.ms_stride_t & 1)))
+      return fail("ms_out must be 16-byte aligned with even strides (vector stores)");
+  }
+  if (a.B > (int64_t)kBlock * 0x7fffffffLL) return fail("B too large for one launch");
+  cudaError_t e = dispatch(a, s);
+  if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// batched quadrature kernel (mfs/one_dim/quadtures.py:83-133)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(kBlock) quadrature_kernel(int64_t B, const double* __restrict__ ms,
+                                                            const double* __restrict__ mean,
+                                                            const double* __restrict__ scale, int sort_nodes,
+                                                            double* __restrict__ weights, double* __restrict__ nodes) {
+  const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (b >= B) return;
+  double m[2 * N], w[N], x[N];
+#pragma unroll
+  for (int p = 0; p < 2 * N; ++p) m[p] = ms[b * 2 * N + p];
+  const bool ok = moment_quadrature<N>(m, mean ? mean[b] : 0.0, scale ? scale[b] : 1.0, w, x);
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { w[i] = nan(""); x[i] = nan(""); }
+  } else if (sort_nodes) {
+    // odd-even transposition network on (x, w): N rounds, compile-time indices
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+      for (int i = (r & 1); i + 1 < N; i += 2) {
+        if (x[i] > x[i + 1]) {
+          const double tx = x[i]; x[i] = x[i + 1]; x[i + 1] = tx;
+          const double tw = w[i]; w[i] = w[i + 1]; w[i + 1] = tw;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { weights[b * N + i] = w[i]; nodes[b * N + i] = x[i]; }
+}
+
+template <int N>
+static cudaError_t launch_quadrature(int64_t B, const double* ms, const double* mean, const double* scale, int sort,
+                                     double* w, double* x, cudaStream_t s) {
+  const unsigned grid = (unsigned)((B + kBlock - 1) / kBlock);
+  quadrature_kernel<N><<<grid, kBlock, 0, s>>>(B, ms, mean, scale, sort, w, x);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FP64 FMA peak micro-benchmark: 8 independent accumulator chains per thread, no memory traffic.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 12345.678) sink[0] = r;  // never true; keeps the chains alive
+}
+
+}  // namespace mfs
+
+using namespace mfs;
+
+extern "C" {
+
+int mfs_abi_version(void) { return MFS_ABI_VERSION; }
+
+const char* mfs_last_error(void) { return g_err.c_str(); }
+
+int64_t mfs_launch_count(void) { return g_launches.load(); }
+
+int mfs_functor_lookup(const char* kind, const char* name, int32_t* id) {
+  struct Entry { const char* kind; const char* name; int id; };
+  static const Entry table[] = {
+      {"mode", "raw", MFS_MODE_RAW}, {"mode", "central", MFS_MODE_CENTRAL}, {"mode", "scaled", MFS_MODE_SCALED},
+      {"trans", "tme", MFS_TRANS_TME}, {"trans", "tme_normal", MFS_TRANS_TME_NORMAL}, {"trans", "euler", MFS_TRANS_EULER},
+      {"trans", "normal_affine", MFS_TRANS_NORMAL_AFFINE},
+      {"drift", "benes", MFS_DRIFT_BENES}, {"drift", "well", MFS_DRIFT_WELL}, {"drift", "linear", MFS_DRIFT_LINEAR},
+      {"meas", "bernoulli_logistic_cubic", MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC},
+      {"meas", "poisson_softplus", MFS_MEAS_POISSON_SOFTPLUS}, {"meas", "gaussian", MFS_MEAS_GAUSSIAN},
+  };
+  if (!kind || !name || !id) return fail("mfs_functor_lookup: NULL argument");
+  for (const Entry& e : table)
+    if (!strcmp(e.kind, kind) && !strcmp(e.name, name)) { *id = e.id; return 0; }
+  return fail("unknown %s functor '%s'", kind, name);
+}
+
+int mfs_filter_1d(const mfs_filter1d_args* a, void* stream) {
+  if (int rc = validate(a)) return rc;
+  return launch_device(*a, static_cast<cudaStream_t>(stream));
+}
+
+int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_filters) {
+  if (int rc = validate(a)) return rc;
+  if (a->B == 0) return 0;
+  const int M = 2 * a->N;
+  const int64_t T = a->T;
+  if (a->T > 0 && (a->ys_stride_t != 1 || a->ys_stride_b != T)) return fail("host ys must be contiguous (B, T)");
+  if (a->out_mode == MFS_OUT_FULL && (a->ms_stride_t != M || a->ms_stride_b != T * M || a->aux_stride_b != T))
+    return fail("host outputs must be contiguous (B, T, 2N) / (B, T)");
+  if (a->out_mode == MFS_OUT_LAST && (a->ms_stride_b != M || a->aux_stride_b != 1))
+    return fail("host outputs must be contiguous (B, 2N) / (B,)");
+  MFS_CUDA(cudaSetDevice(device));
+
+  const int esz = ys_elem_size(a->ys_dtype);
+  if (chunk_filters <= 0) {
+    // aim for ~256 MiB of output per chunk, at least 8 waves of CTAs on 148 SMs
+    const int64_t per_filter = (a->out_mode == MFS_OUT_FULL ? T * (M + 2) * 8 : (M + 4) * 8) + T * esz;
+    chunk_filters = (256LL << 20) / (per_filter > 0 ? per_filter : 1);
+    if (chunk_filters < 148LL * 4 * kBlock) chunk_filters = 148LL * 4 * kBlock;
+  }
+  chunk_filters = (chunk_filters + kBlock - 1) / kBlock * kBlock;
+  if (chunk_filters > a->B) chunk_filters = a->B;
+  const int64_t C = chunk_filters;
+
+  struct Slot {
+    cudaStream_t s = nullptr;
+    void* ys = nullptr;
+    double *ms0 = nullptr, *mean0 = nullptr, *scale0 = nullptr, *tprm = nullptr, *mprm = nullptr;
+    double *ms_out = nullptr, *mean_out = nullptr, *scale_out = nullptr, *nell = nullptr;
+    int32_t* status = nullptr;
+  } slot[2];
+  const bool per_ms0 = a->ms0_stride != 0, per_mean0 = a->mean0 && a->mean0_stride != 0,
+             per_scale0 = a->scale0 && a->scale0_stride != 0, per_t = a->trans_param_stride != 0,
+             per_m = a->meas_param_stride != 0;
+  const int64_t out_ms = a->out_mode == MFS_OUT_FULL ? C * T * M : a->out_mode == MFS_OUT_LAST ? C * M : 0;
+  const int64_t out_aux = a->out_mode == MFS_OUT_FULL ? C * T : a->out_mode == MFS_OUT_LAST ? C : 0;
+
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (Slot& k : slot) {
+      if (k.s) cudaStreamSynchronize(k.s);
+      cudaFree(k.ys); cudaFree(k.ms0); cudaFree(k.mean0); cudaFree(k.scale0); cudaFree(k.tprm); cudaFree(k.mprm);
+      cudaFree(k.ms_out); cudaFree(k.mean_out); cudaFree(k.scale_out); cudaFree(k.nell); cudaFree(k.status);
+      if (k.s) cudaStreamDestroy(k.s);
+    }
+  };
+#define MFS_TRY(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) { rc = fail("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return rc; } \
+  } while (0)
+
+  const int nslots = a->B > C ? 2 : 1;
+  for (int k = 0; k < nslots; ++k) {
+    Slot& s = slot[k];
+    MFS_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+    if (T > 0) MFS_TRY(cudaMalloc(&s.ys, (size_t)(C * T * esz)));
+    MFS_TRY(cudaMalloc(&s.ms0, sizeof(double) * (per_ms0 ? C * M : M)));
+    if (a->mean0) MFS_TRY(cudaMalloc(&s.mean0, sizeof(double) * (per_mean0 ? C : 1)));
+    if (a->scale0) MFS_TRY(cudaMalloc(&s.scale0, sizeof(double) * (per_scale0 ? C : 1)));
+    MFS_TRY(cudaMalloc(&s.tprm, sizeof(double) * MFS_MAX_PARAMS * (per_t ? C : 1)));
+    MFS_TRY(cudaMalloc(&s.mprm, sizeof(double) * MFS_MAX_PARAMS * (per_m ? C : 1)));
+    if (out_ms) MFS_TRY(cudaMalloc(&s.ms_out, sizeof(double) * out_ms));
+    if (out_aux && a->mean_out) MFS_TRY(cudaMalloc(&s.mean_out, sizeof(double) * out_aux));
+    if (out_aux && a->scale_out) MFS_TRY(cudaMalloc(&s.scale_out, sizeof(double) * out_aux));
+    MFS_TRY(cudaMalloc(&s.nell, sizeof(double) * C));
+    if (a->status_out) MFS_TRY(cudaMalloc(&s.status, sizeof(int32_t) * C));
+  }
+
+  int k = 0;
+  for (int64_t b0 = 0; b0 < a->B; b0 += C, k ^= (nslots - 1)) {
+    Slot& s = slot[k];
+    const int64_t n = (a->B - b0 < C) ? a->B - b0 : C;
+    const auto H2D = cudaMemcpyHostToDevice;
+    const auto D2H = cudaMemcpyDeviceToHost;
+    // stream order makes the reuse of this slot's buffers safe: its previous D2H copies precede these H2D copies
+    if (T > 0)
+      MFS_TRY(cudaMemcpyAsync(s.ys, static_cast<const char*>(a->ys) + b0 * T * esz, (size_t)(n * T * esz), H2D, s.s));
+    MFS_TRY(cudaMemcpyAsync(s.ms0, a->ms0 + (per_ms0 ? b0 * a->ms0_stride : 0), sizeof(double) * (per_ms0 ? n * M : M), H2D, s.s));
+    if (a->mean0) MFS_TRY(cudaMemcpyAsync(s.mean0, a->mean0 + (per_mean0 ? b0 : 0), sizeof(double) * (per_mean0 ? n : 1), H2D, s.s));
+    if (a->scale0) MFS_TRY(cudaMemcpyAsync(s.scale0, a->scale0 + (per_scale0 ? b0 : 0), sizeof(double) * (per_scale0 ? n : 1), H2D, s.s));
+    MFS_TRY(cudaMemcpyAsync(s.tprm, a->trans_params + (per_t ? b0 * a->trans_param_stride : 0), sizeof(double) * MFS_MAX_PARAMS * (per_t ? n : 1), H2D, s.s));
+    MFS_TRY(cudaMemcpyAsync(s.mprm, a->meas_params + (per_m ? b0 * a->meas_param_stride : 0), sizeof(double) * MFS_MAX_PARAMS * (per_m ? n : 1), H2D, s.s));
+
+    mfs_filter1d_args d = *a;
+    d.B = n;
+    d.ys = s.ys;
+    d.ms0 = s.ms0; d.ms0_stride = per_ms0 ? M : 0;
+    d.mean0 = s.mean0; d.mean0_stride = per_mean0 ? 1 : 0;
+    d.scale0 = s.scale0; d.scale0_stride = per_scale0 ? 1 : 0;
+    d.trans_params = s.tprm; d.trans_param_stride = per_t ? MFS_MAX_PARAMS : 0;
+    d.meas_params = s.mprm; d.meas_param_stride = per_m ? MFS_MAX_PARAMS : 0;
+    d.ms_out = s.ms_out; d.mean_out = s.mean_out; d.scale_out = s.scale_out;
+    d.nell_out = s.nell; d.status_out = s.status;
+    if (per_ms0 && a->ms0_stride != M) { rc = fail("host ms0 must be contiguous (B, 2N)"); cleanup(); return rc; }
+    if ((per_t && a->trans_param_stride != MFS_MAX_PARAMS) || (per_m && a->meas_param_stride != MFS_MAX_PARAMS)) {
+      rc = fail("host params must be contiguous (B, %d)", MFS_MAX_PARAMS); cleanup(); return rc;
+    }
+    if (launch_device(d, s.s)) { cleanup(); return -1; }
+
+    if (a->out_mode == MFS_OUT_FULL) {
+      MFS_TRY(cudaMemcpyAsync(a->ms_out + b0 * T * M, s.ms_out, sizeof(double) * n * T * M, D2H, s.s));
+      if (a->mean_out) MFS_TRY(cudaMemcpyAsync(a->mean_out + b0 * T, s.mean_out, sizeof(double) * n * T, D2H, s.s));
+      if (a->scale_out) MFS_TRY(cudaMemcpyAsync(a->scale_out + b0 * T, s.scale_out, sizeof(double) * n * T, D2H, s.s));
+    } else if (a->out_mode == MFS_OUT_LAST) {
+      MFS_TRY(cudaMemcpyAsync(a->ms_out + b0 * M, s.ms_out, sizeof(double) * n * M, D2H, s.s));
+      if (a->mean_out) MFS_TRY(cudaMemcpyAsync(a->mean_out + b0, s.mean_out, sizeof(double) * n, D2H, s.s));
+      if (a->scale_out) MFS_TRY(cudaMemcpyAsync(a->scale_out + b0, s.scale_out, sizeof(double) * n, D2H, s.s));
+    }
+    MFS_TRY(cudaMemcpyAsync(a->nell_out + b0, s.nell, sizeof(double) * n, D2H, s.s));
+    if (a->status_out) MFS_TRY(cudaMemcpyAsync(a->status_out + b0, s.status, sizeof(int32_t) * n, D2H, s.s));
+  }
+  for (int i = 0; i < nslots; ++i) MFS_TRY(cudaStreamSynchronize(slot[i].s));
+  cleanup();
+  return 0;
+#undef MFS_TRY
+}
+
+int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
+                             int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream) {
+  if (N < 1 || N > MFS_MAX_N) return fail("N=%d outside [1, %d]", N, MFS_MAX_N);
+  if (ldl) return fail("ldl=True is not implemented in this build");
+  if (B < 0) return fail("negative B");
+  if (B == 0) return 0;
+  if (!ms || !weights || !nodes) return fail("NULL pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (N) {
+#define MFS_CASE(n) case n: e = launch_quadrature<n>(B, ms, mean, scale, sort_nodes, weights, nodes, s); break;
+    MFS_CASE(1) MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
+    MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
+#undef MFS_CASE
+  }
+  if (e != cudaSuccess) return fail("quadrature launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_fp64_peak(int device, int32_t iters, double* flops, double* ms) {
+  if (!flops) return fail("flops is NULL");
+  MFS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MFS_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* sink = nullptr;
+  MFS_CUDA(cudaMalloc(&sink, sizeof(double)));
+  const int grid = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  MFS_CUDA(cudaEventCreate(&e0));
+  MFS_CUDA(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<grid, 256>>>(iters / 4 + 1, 1.0, sink);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    MFS_CUDA(cudaEventRecord(e0));
+    fp64_peak_kernel<<<grid, 256>>>(iters, 1.0, sink);
+    MFS_CUDA(cudaEventRecord(e1));
+    MFS_CUDA(cudaEventSynchronize(e1));
+    float t;
+    MFS_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (t < best) best = t;
+  }
+  g_launches.fetch_add(6, std::memory_order_relaxed);
+  MFS_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  const double fmas = (double)grid * 256.0 * (double)iters * 16.0 * 8.0;
+  *flops = 2.0 * fmas / (best * 1e-3);
+  if (ms) *ms = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+"""Host-side mirror of ``mfs/one_dim/filtering.py``: same names, positional signatures, return tuples and warnings;
+the scan runs in one CUDA kernel launch for the whole batch (``mfs_b200/csrc/filter1d.cuh``).
+
+Extension over the reference: leading batch axes.  ``ys`` may be ``(..., T)`` and the initial moments ``(2N,)`` or
+``(..., 2N)``; functor parameters may be per-filter arrays.  Every filter of the batch is independent.
+
+Where the data lives decides the path (there is no CPU compute path):
+  * ``ys`` is a ``torch`` CUDA tensor  -> device pointers are handed to ``mfs_filter_1d`` on torch's current stream,
+    outputs are CUDA tensors (asynchronous w.r.t. the host);
+  * ``ys`` is a NumPy array / CPU tensor -> ``mfs_filter_1d_host`` stages chunks H2D -> kernel -> D2H on ``device``
+    and returns NumPy arrays.
+"""
+import ctypes
+import warnings
+from typing import Optional
+
+import numpy as np
+
+from .. import _lib
+from ..functors import TransitionFunctor, MeasurementFunctor, pack_params
+
+__all__ = ['moment_filter_rms', 'moment_filter_cms', 'moment_filter_scms']
+
+
+def _is_torch_cuda(x) -> bool:
+    return type(x).__module__.startswith('torch') and getattr(x, 'is_cuda', False)
+
+
+def _check_transition(fn, role: str, argname: str) -> TransitionFunctor:
+    if not isinstance(fn, TransitionFunctor):
+        raise TypeError(f'{argname} must be a TransitionFunctor handle produced by mfs_b200.one_dim.moments.'
+                        f'sde_cond_moments_*; Python callables cannot run inside the CUDA kernel (no CPU fallback).')
+    if fn.role != role:
+        raise ValueError(f'{argname} must be the {role!r} member of the factory tuple, got {fn.role!r}')
+    return fn
+
+
+def _check_measurement(fn) -> MeasurementFunctor:
+    if not isinstance(fn, MeasurementFunctor):
+        raise TypeError('measurement_cond_pdf must be a MeasurementFunctor handle (bernoulli_logistic_cubic, '
+                        'poisson_softplus, gaussian); Python callables cannot run inside the CUDA kernel.')
+    return fn
+
+
+def _ys_dtype_code(dtype_name: str) -> int:
+    name = dtype_name.replace('torch.', '')
+    if name not in _lib.YS_DTYPE:
+        raise TypeError(f'ys dtype {dtype_name} not supported (uint8 / bool / int32 / float64)')
+    return _lib.YS_DTYPE[name]
+
+
+def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stable: bool, history: str,
+         device: Optional[int], return_status: bool, chunk_filters: int):
+    if history not in _lib.OUT_MODE:
+        raise ValueError(f"history must be one of {sorted(_lib.OUT_MODE)}")
+    on_device = _is_torch_cuda(ys)
+    if not on_device and type(ys).__module__.startswith('torch'):
+        ys = ys.numpy()
+    if not on_device:
+        ys = np.asarray(ys)
+        if ys.dtype == np.bool_:
+            ys = ys.view(np.uint8)
+        elif ys.dtype == np.int64:
+            ys = ys.astype(np.int32)
+        elif ys.dtype in (np.float32, np.float16):
+            ys = ys.astype(np.float64)
+    if ys.ndim < 1:
+        raise ValueError('ys must have shape (..., T)')
+    batch_shape = tuple(ys.shape[:-1])
+    T = int(ys.shape[-1])
+    B = int(np.prod(batch_shape)) if batch_shape else 1
+
+    ms0_np = np.asarray(ms0.cpu() if _is_torch_cuda(ms0) else ms0, dtype=np.float64)
+    num_moments = ms0_np.shape[-1]
+    if num_moments % 2 != 0:
+        warnings.warn(f'The order of moments {num_moments - 1} is not odd.')      # mfs/one_dim/filtering.py:65-66
+    N = num_moments // 2
+    if N < 2 or N > _lib.MAX_N:
+        raise ValueError(f'number of moments {num_moments} outside [4, {2 * _lib.MAX_N}]')
+    M = 2 * N
+
+    def per_filter(arr, trailing):
+        """-> (contiguous float64 array (rows, *trailing), stride in elements)"""
+        arr = np.asarray(arr.cpu() if _is_torch_cuda(arr) else arr, dtype=np.float64)
+        if arr.shape == trailing:
+            return np.ascontiguousarray(arr.reshape((1,) + trailing)), 0
+        full = np.broadcast_to(arr, batch_shape + trailing).reshape((B,) + trailing)
+        return np.ascontiguousarray(full), int(np.prod(trailing)) if trailing else 1
+
+    ms0_tab, ms0_stride = per_filter(ms0_np[..., :M], (M,))
+    mean0_tab = scale0_tab = None
+    mean0_stride = scale0_stride = 0
+    if mode != 'raw':
+        mean0_tab, mean0_stride = per_filter(mean0, ())
+    if mode == 'scaled':
+        scale0_tab, scale0_stride = per_filter(scale0, ())
+    tprm, tstride = pack_params(spec.packed_params(), batch_shape)
+    mprm, mstride = pack_params(meas.params, batch_shape)
+
+    a = _lib.Filter1dArgs()
+    a.abi_version, a.mode, a.N, a.stable = _lib.ABI_VERSION, _lib.MODE[mode], N, int(bool(stable))
+    a.B, a.T = B, T
+    a.trans_id, a.drift_id = _lib.TRANS[spec.family], _lib.DRIFT[spec.drift.name]
+    a.tme_order, a.meas_id = spec.order, _lib.MEAS[meas.name]
+    a.dt, a.dispersion = spec.dt, spec.dispersion
+    a.trans_param_stride, a.meas_param_stride = tstride, mstride
+    a.ms0_stride, a.mean0_stride, a.scale0_stride = ms0_stride, mean0_stride, scale0_stride
+    a.out_mode = _lib.OUT_MODE[history]
+    a.ys_stride_b, a.ys_stride_t = T, 1
+
+    L = _lib.lib()
+    if on_device:
+        import torch
+        dev = ys.device
+        ys_c = ys.reshape(B, T)
+        if ys_c.dtype == torch.bool:
+            ys_c = ys_c.view(torch.uint8)
+        ys_c = ys_c.contiguous()
+        a.ys_dtype = _ys_dtype_code(str(ys_c.dtype))
+        keep = [ys_c]
+
+        def to_dev(tab):
+            t = torch.from_numpy(tab).to(dev)
+            keep.append(t)
+            return t.data_ptr()
+
+        a.ys = ys_c.data_ptr()
+        a.ms0, a.trans_params, a.meas_params = to_dev(ms0_tab), to_dev(tprm), to_dev(mprm)
+        if mean0_tab is not None:
+            a.mean0 = to_dev(mean0_tab)
+        if scale0_tab is not None:
+            a.scale0 = to_dev(scale0_tab)
+        f64 = dict(dtype=torch.float64, device=dev)
+        nell = torch.empty(B, **f64)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        ms_out = mean_out = scale_out = None
+        if history == 'full':
+            ms_out = torch.empty((B, T, M), **f64)
+            a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = T * M, M, T
+            aux_shape = (B, T)
+        elif history == 'last':
+            ms_out = torch.empty((B, M), **f64)
+            a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = M, 0, 1
+            aux_shape = (B,)
+        if ms_out is not None:
+            a.ms_out = ms_out.data_ptr()
+            if mode != 'raw':
+                mean_out = torch.empty(aux_shape, **f64)
+                a.mean_out = mean_out.data_ptr()
+            if mode == 'scaled':
+                scale_out = torch.empty(aux_shape, **f64)
+                a.scale_out = scale_out.data_ptr()
+        a.nell_out, a.status_out = nell.data_ptr(), status.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(L.mfs_filter_1d(ctypes.byref(a), ctypes.c_void_p(stream)))
+        for t in keep:   # inputs must outlive the asynchronous kernel
+            t.record_stream(torch.cuda.current_stream(dev))
+        reshape = lambda t, tail: None if t is None else t.reshape(batch_shape + tail)
+    else:
+        ys_c = np.ascontiguousarray(ys.reshape(B, T))
+        a.ys_dtype = _ys_dtype_code(str(ys_c.dtype))
+        ptr = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+        a.ys = ptr(ys_c)
+        a.ms0, a.trans_params, a.meas_params = ptr(ms0_tab), ptr(tprm), ptr(mprm)
+        if mean0_tab is not None:
+            a.mean0 = ptr(mean0_tab)
+        if scale0_tab is not None:
+            a.scale0 = ptr(scale0_tab)
+        nell = np.empty(B, dtype=np.float64)
+        status = np.empty(B, dtype=np.int32)
+        ms_out = mean_out = scale_out = None
+        if history == 'full':
+            ms_out = np.empty((B, T, M), dtype=np.float64)
+            a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = T * M, M, T
+            aux_shape = (B, T)
+        elif history == 'last':
+            ms_out = np.empty((B, M), dtype=np.float64)
+            a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = M, 0, 1
+            aux_shape = (B,)
+        if ms_out is not None:
+            a.ms_out = ptr(ms_out)
+            if mode != 'raw':
+                mean_out = np.empty(aux_shape, dtype=np.float64)
+                a.mean_out = ptr(mean_out)
+            if mode == 'scaled':
+                scale_out = np.empty(aux_shape, dtype=np.float64)
+                a.scale_out = ptr(scale_out)
+        a.nell_out, a.status_out = ptr(nell), ptr(status)
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        _lib.check(L.mfs_filter_1d_host(ctypes.byref(a), int(device), int(chunk_filters)))
+        reshape = lambda t, tail: None if t is None else t.reshape(batch_shape + tail)
+
+    hist_tail = (T,) if history == 'full' else ()
+    out = {
+        'ms': reshape(ms_out, hist_tail + (M,)),
+        'mean': reshape(mean_out, hist_tail),
+        'scale': reshape(scale_out, hist_tail),
+        'nell': reshape(nell, ()),
+        'status': reshape(status, ()),
+    }
+    return out
+
+
+def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, stable: bool = False, *,
+                      history: str = 'full', device: Optional[int] = None, return_status: bool = False,
+                      chunk_filters: int = 0):
+    """Raw-moment filter, mirror of ``mfs/one_dim/filtering.py:32-89``.
+
+    Returns ``(rmss (..., T, 2N), nell (...))`` like the reference (``history='last'`` -> ``(..., 2N)``,
+    ``'none'`` -> ``None``); with ``return_status=True`` a third element holds the first failed step per filter
+    (-1: none).  A filter whose moment matrix stops being positive definite yields NaN from that step on, exactly like
+    the JAX scan.
+    """
+    fn = _check_transition(state_cond_raw_moments, 'raw', 'state_cond_raw_moments')
+    out = _run('raw', fn.spec, _check_measurement(measurement_cond_pdf), rms0, None, None, ys, stable, history,
+               device, return_status, chunk_filters)
+    res = (out['ms'], out['nell'])
+    return res + (out['status'],) if return_status else res
+
+
+def moment_filter_cms(state_cond_central_moments, state_cond_mean, measurement_cond_pdf, cms0, mean0, ys,
+                      stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
+                      return_status: bool = False, chunk_filters: int = 0):
+    """Central-moment filter, mirror of ``mfs/one_dim/filtering.py:92-161``.  Returns ``(cmss, means, nell)``."""
+    fn = _check_transition(state_cond_central_moments, 'central', 'state_cond_central_moments')
+    fm = _check_transition(state_cond_mean, 'mean', 'state_cond_mean')
+    if fm.spec is not fn.spec:
+        raise ValueError('state_cond_central_moments and state_cond_mean must come from the same factory call')
+    out = _run('central', fn.spec, _check_measurement(measurement_cond_pdf), cms0, mean0, None, ys, stable, history,
+               device, return_status, chunk_filters)
+    res = (out['ms'], out['mean'], out['nell'])
+    return res + (out['status'],) if return_status else res
+
+
+def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, measurement_cond_pdf, scms0, mean0,
+                       scale0, ys, stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
+                       return_status: bool = False, chunk_filters: int = 0):
+    """Scaled-central-moment filter, mirror of ``mfs/one_dim/filtering.py:164-240``.
+    Returns ``(scmss, means, scales, nell)``."""
+    fn = _check_transition(state_cond_scaled_central_moments, 'scaled', 'state_cond_scaled_central_moments')
+    fm = _check_transition(state_cond_mean_var, 'mean_var', 'state_cond_mean_var')
+    if fm.spec is not fn.spec:
+        raise ValueError('state_cond_scaled_central_moments and state_cond_mean_var must come from the same factory')
+    out = _run('scaled', fn.spec, _check_measurement(measurement_cond_pdf), scms0, mean0, scale0, ys, stable,
+               history, device, return_status, chunk_filters)
+    res = (out['ms'], out['mean'], out['scale'], out['nell'])
+    return res + (out['status'],) if return_status else res

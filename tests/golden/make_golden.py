@@ -1,0 +1,209 @@
+"""
+Generate the golden fixtures under ``tests/golden/`` by EXECUTING THE REFERENCE'S OWN SOURCE FILES.
+
+Run in the build container only (needs ``/root/reference``; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+The reference is pure JAX and JAX is not installed, so its modules are imported on top of the NumPy-backed shim in
+``_jax_shim.py`` (float64, LAPACK potrf/trtrs/syevd = the routines XLA:CPU dispatches to).  What runs is the
+reference's code, unmodified, from where it lies:
+
+  mfs/one_dim/quadtures.py   moment_quadrature            -> golden_quadrature_1d.npz
+  mfs/one_dim/filtering.py   moment_filter_{rms,cms,scms} -> golden_filter_1d_*.npz
+  mfs/one_dim/moments.py     raw_to_central, raw_to_scaled, sde_cond_moments_euler, raw_moment_of_normal
+  mfs/one_dim/ss_models.py   benes_bernoulli (constants, logistic, Bernoulli pmf), well_poisson
+  mfs/utils.py               GaussianSum1D.new, ldl, ldl_chol
+  mfs/multi_dims/multi_indices.py   (pure NumPy)          -> golden_multi_indices.npz
+  mfs/multi_dims/moments.py  Kan--Magnus NumPy branches   -> golden_kan_moments.npz
+  mfs/multi_dims/quadratures.py, filtering.py             -> golden_nd_*.npz
+
+The third-party ``tme`` package is absent, so fixtures whose transition moments are TME expansions take those
+callables from ``oracle/mfs_oracle.py`` (definition-driven restatement) and are labelled ``*_tme*``: they pin the
+filter recursion + quadrature of the reference, not ``tme`` itself.  Fixtures labelled ``*_euler*`` are 100 %
+reference code (Euler--Maruyama + Normal transition, ``mfs/one_dim/moments.py:222-255``).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('MFS_REFERENCE', '/root/reference')
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import _jax_shim  # noqa: E402
+
+_jax_shim.install()
+sys.path.insert(0, REF)
+
+import jax.numpy as jnp  # noqa: E402  (the shim)
+from mfs.one_dim.quadtures import moment_quadrature  # noqa: E402
+from mfs.one_dim.filtering import moment_filter_rms, moment_filter_cms, moment_filter_scms  # noqa: E402
+from mfs.one_dim.moments import (raw_to_central, raw_to_scaled, raw_moment_of_normal,  # noqa: E402
+                                 sde_cond_moments_euler, central_to_raw)
+from mfs.one_dim.ss_models import benes_bernoulli, well_poisson  # noqa: E402
+from mfs.utils import GaussianSum1D, ldl_chol  # noqa: E402
+
+from oracle import mfs_oracle as O  # noqa: E402
+
+
+def synth_benes_bernoulli(rng, T, dt, n_traj):
+    """Exact Benes law (mixture of two Normals) + Bernoulli(logistic(x^3/5)) observations, uint8 (n_traj, T)."""
+    comp = rng.integers(0, 2, n_traj)
+    x = np.where(comp == 0, -0.5, 0.5) + np.sqrt(0.05) * rng.standard_normal(n_traj)
+    ys = np.empty((n_traj, T), dtype=np.uint8)
+    for t in range(T):
+        s = np.where(rng.random(n_traj) < 0.5 * (1 + np.tanh(x)), 1., -1.)
+        x = x + s * dt + np.sqrt(dt) * rng.standard_normal(n_traj)
+        ys[:, t] = rng.random(n_traj) < 1 / (1 + np.exp(-x ** 3 / 5))
+    return ys
+
+
+def golden_quadrature_1d():
+    out = {}
+    cases = {}
+    # Gaussian m=0.2, v=1.1, n=8 nodes  (tests/test_one_dim_quadrature.py:50-57 setting)
+    rms = np.array([raw_moment_of_normal(0.2, 1.1, p) for p in range(16)])
+    cases['gauss8_raw'] = (rms, 0., 1.)
+    cases['gauss8_central'] = (np.asarray(raw_to_central(jnp.asarray(rms))), 0.2, 1.)
+    cases['gauss8_scaled'] = (np.asarray(raw_to_scaled(jnp.asarray(rms))), 0.2, np.sqrt(1.1))
+    for N in (2, 3, 5, 8, 10, 12, 15):
+        ic = GaussianSum1D.new(means=jnp.array([-0.5, 0.5]), variances=jnp.array([0.05, 0.05]),
+                               weights=jnp.array([0.5, 0.5]), N=N)
+        cases[f'mix{N}_raw'] = (np.asarray(ic.rms), 0., 1.)
+        cases[f'mix{N}_central'] = (np.asarray(ic.cms), float(ic.mean), 1.)
+        cases[f'mix{N}_scaled'] = (np.asarray(ic.scms), float(ic.mean), float(np.sqrt(ic.variance)))
+    # uniform[-2, 3] moments, N=4 (tests/test_one_dim_quadrature.py:96-113 setting)
+    a, b = -2., 3.
+    cases['uniform4_raw'] = (np.array([(b ** (p + 1) - a ** (p + 1)) / ((p + 1) * (b - a)) for p in range(8)]), 0., 1.)
+    for name, (ms, mean, scale) in cases.items():
+        w, x = moment_quadrature(jnp.asarray(ms), mean, scale, sort_nodes=True)
+        out[f'{name}/ms'], out[f'{name}/mean'], out[f'{name}/scale'] = ms, mean, scale
+        out[f'{name}/weights'], out[f'{name}/nodes'] = np.asarray(w), np.asarray(x)
+        w, x = moment_quadrature(jnp.asarray(ms), mean, scale, sort_nodes=True, ldl=True)
+        out[f'{name}/weights_ldl'], out[f'{name}/nodes_ldl'] = np.asarray(w), np.asarray(x)
+    # A non-PD Hankel matrix: NaN semantics of the reference, and the ldl completion
+    bad = np.array([1., 0., 1., 0., 0.5, 0., 3., 0.])
+    w, x = moment_quadrature(jnp.asarray(bad))
+    out['nonpd/ms'], out['nonpd/weights'], out['nonpd/nodes'] = bad, np.asarray(w), np.asarray(x)
+    G = bad[np.arange(4)[:, None] + np.arange(4)[None, :]]
+    out['nonpd/ldl_chol'] = np.asarray(ldl_chol(jnp.asarray(G)))
+    np.savez_compressed(os.path.join(HERE, 'golden_quadrature_1d.npz'), **out)
+    print('golden_quadrature_1d.npz', len(cases), 'cases')
+
+
+def golden_conversions():
+    out = {}
+    for N in (2, 5, 8):
+        ic = GaussianSum1D.new(means=jnp.array([-0.5, 0.5]), variances=jnp.array([0.05, 0.05]),
+                               weights=jnp.array([0.5, 0.5]), N=N)
+        out[f'mix{N}/rms'], out[f'mix{N}/cms'], out[f'mix{N}/scms'] = map(np.asarray, (ic.rms, ic.cms, ic.scms))
+        out[f'mix{N}/mean'], out[f'mix{N}/variance'] = float(ic.mean), float(ic.variance)
+    rms = np.array([raw_moment_of_normal(1.1, 4.9, p) for p in range(10)])
+    out['normal/rms'] = rms
+    out['normal/raw_to_central'] = np.asarray(raw_to_central(jnp.asarray(rms)))
+    out['normal/raw_to_scaled'] = np.asarray(raw_to_scaled(jnp.asarray(rms)))
+    out['normal/central_to_raw'] = np.asarray(central_to_raw(jnp.asarray(out['normal/raw_to_central']), 1.1))
+    np.savez_compressed(os.path.join(HERE, 'golden_conversions_1d.npz'), **out)
+    print('golden_conversions_1d.npz')
+
+
+def golden_filter_1d():
+    rng = np.random.Generator(np.random.PCG64(666))
+    n_traj = 4
+    for N in (5, 8):
+        dt, T, ts, init_cond, drift, dispersion, logistic, pmf, _ = benes_bernoulli(N)
+        ys_all = synth_benes_bernoulli(rng, T, dt, n_traj)
+        out = {'ys': ys_all, 'rms0': np.asarray(init_cond.rms), 'cms0': np.asarray(init_cond.cms),
+               'scms0': np.asarray(init_cond.scms), 'mean0': float(init_cond.mean),
+               'scale0': float(np.sqrt(init_cond.variance)), 'dt': dt}
+
+        # (a) 100 % reference code: Euler--Maruyama + Normal transition moments
+        e_rms, e_cms, e_scms, e_mean, e_mean_var = sde_cond_moments_euler(drift, dispersion, dt, N)
+        # (b) reference filter + quadrature, TME-2 / TME-3 transition moments from the oracle restatement
+        variants = {'euler': (e_rms, e_cms, e_scms, e_mean, e_mean_var)}
+        for order in (2, 3):
+            variants[f'tme{order}'] = O.sde_cond_moments_tme('benes', (), 1., dt, order, 2 * N)
+        variants['tme_normal3'] = O.sde_cond_moments_tme_normal('benes', (), 1., dt, 3, N)
+
+        for vname, (f_rms, f_cms, f_scms, f_mean, f_mean_var) in variants.items():
+            for k in range(n_traj):
+                ys = jnp.asarray(ys_all[k])
+                rmss, nell = moment_filter_rms(f_rms, pmf, init_cond.rms, ys)
+                out[f'{vname}/rms/{k}/rmss'], out[f'{vname}/rms/{k}/nell'] = np.asarray(rmss), float(nell)
+                cmss, means, nell = moment_filter_cms(f_cms, f_mean, pmf, init_cond.cms, init_cond.mean, ys)
+                out[f'{vname}/cms/{k}/cmss'], out[f'{vname}/cms/{k}/means'] = np.asarray(cmss), np.asarray(means)
+                out[f'{vname}/cms/{k}/nell'] = float(nell)
+                if vname in ('tme2', 'tme3'):   # the Normal factories' scaled variant divides by prod(scale**k): skip
+                    scmss, means, scales, nell = moment_filter_scms(f_scms, f_mean_var, pmf, init_cond.scms,
+                                                                    init_cond.mean, jnp.sqrt(init_cond.variance), ys)
+                    out[f'{vname}/scms/{k}/scmss'] = np.asarray(scmss)
+                    out[f'{vname}/scms/{k}/means'], out[f'{vname}/scms/{k}/scales'] = map(np.asarray, (means, scales))
+                    out[f'{vname}/scms/{k}/nell'] = float(nell)
+            # stable=True (LDL completion) on the first trajectory
+            rmss, nell = moment_filter_rms(f_rms, pmf, init_cond.rms, jnp.asarray(ys_all[0]), stable=True)
+            out[f'{vname}/rms_stable/0/rmss'], out[f'{vname}/rms_stable/0/nell'] = np.asarray(rmss), float(nell)
+        np.savez_compressed(os.path.join(HERE, f'golden_filter_1d_benes_N{N}.npz'), **out)
+        print(f'golden_filter_1d_benes_N{N}.npz')
+
+    # OU + Gaussian likelihood, the reference's own test input (tests/test_filtering.py:18-37; numpy seed 666)
+    import math
+    np.random.seed(666)
+    dt, T = 1e-2, 100
+    ts = np.linspace(dt, dt * T, T)
+    ell, sigma = 1., 0.5
+    cov = np.exp(-np.abs(ts[None, :] - ts[:, None]) / ell) * sigma ** 2
+    ys = np.linalg.cholesky(cov) @ np.random.randn(T) + np.random.randn(T)
+    b = math.sqrt(2) * sigma / math.sqrt(ell)
+    from jax.scipy.stats import norm
+    pdf = lambda y, x: jnp.squeeze(norm.pdf(y, x, 1.))
+    out = {'ys': ys, 'ell': ell, 'sigma': sigma, 'dt': dt}
+    for N, order, mean0, var0 in ((10, 3, 0.1, 0.1), (4, 2, 0., 0.5)):
+        rms0 = jnp.array([raw_moment_of_normal(mean0, var0, p) for p in range(2 * N)])
+        f_rms, f_cms, f_scms, f_mean, f_mean_var = O.sde_cond_moments_tme('ou', (ell,), b, dt, order, 2 * N)
+        rmss, nell = moment_filter_rms(f_rms, pdf, rms0, jnp.asarray(ys))
+        out[f'N{N}/rms0'], out[f'N{N}/rmss'], out[f'N{N}/nell'] = np.asarray(rms0), np.asarray(rmss), float(nell)
+        cmss, means, nell = moment_filter_cms(f_cms, f_mean, pdf, raw_to_central(rms0), mean0, jnp.asarray(ys))
+        out[f'N{N}/cmss'], out[f'N{N}/means'], out[f'N{N}/nell_c'] = np.asarray(cmss), np.asarray(means), float(nell)
+        out[f'N{N}/mean0'], out[f'N{N}/var0'], out[f'N{N}/order'] = mean0, var0, order
+    np.savez_compressed(os.path.join(HERE, 'golden_filter_1d_ou.npz'), **out)
+    print('golden_filter_1d_ou.npz')
+
+    # well--Poisson, central, Euler + the oracle's TME-normal-2  (dardel/parameter_estimation/mf.py:50-53 setting)
+    N = 5
+    dt, T, ts, init_cond, drift, dispersion, emission, pmf, _ = well_poisson(3., N)
+    T = 200
+    theta = (3., 3.)
+    rng = np.random.Generator(np.random.PCG64(667))
+    x = 0.5
+    ys = np.empty(T, dtype=np.int32)
+    for t in range(T):
+        for _ in range(10):
+            x = x + x * (1 - theta[0] * x ** 2) * dt / 10 + np.sqrt(dt / 10) * rng.standard_normal()
+        ys[t] = rng.poisson(np.log1p(np.exp(theta[1] * x)))
+    out = {'ys': ys, 'theta': np.array(theta), 'cms0': np.asarray(init_cond.cms), 'mean0': float(init_cond.mean),
+           'rms0': np.asarray(init_cond.rms), 'dt': dt}
+    e = sde_cond_moments_euler(lambda u: drift(u, theta[0]), dispersion, dt, N)
+    tn = O.sde_cond_moments_tme_normal('well', (theta[0],), 1., dt, 2, N)
+    for vname, fam in (('euler', e), ('tme_normal2', tn)):
+        cmss, means, nell = moment_filter_cms(fam[1], fam[3], lambda y, u: pmf(y, u, theta[1]), init_cond.cms,
+                                              init_cond.mean, jnp.asarray(ys))
+        out[f'{vname}/cmss'], out[f'{vname}/means'], out[f'{vname}/nell'] = np.asarray(cmss), np.asarray(means), \
+            float(nell)
+        rmss, nell = moment_filter_rms(fam[0], lambda y, u: pmf(y, u, theta[1]), init_cond.rms, jnp.asarray(ys))
+        out[f'{vname}/rmss'], out[f'{vname}/nell_r'] = np.asarray(rmss), float(nell)
+    np.savez_compressed(os.path.join(HERE, 'golden_filter_1d_well.npz'), **out)
+    print('golden_filter_1d_well.npz')
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d']
+    if 'quadrature' in which:
+        golden_quadrature_1d()
+    if 'conversions' in which:
+        golden_conversions()
+    if 'filter1d' in which:
+        golden_filter_1d()
