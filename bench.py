@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark: Benes--Bernoulli moment filter, N=8 nodes (16 raw moments), T=1000, 1e6 independent filters per
+GPU (BASELINE.json configs[1]); metric = filter-steps/s (batch x T / time), fp64.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 3 --warmup 3
+    python bench.py --impl reference --steps 2 --warmup 1       # CPU arm: the C restatement of the reference algorithm
+
+One "step" = one pass of the filter over the whole batch (B x T filter-steps, one kernel launch per GPU).
+  value   inputs (ys uint8, 1 GB) resident in HBM, full moment history (B, T, 16) written to HBM, CUDA events on the
+          launching stream, barrier + synchronize on both sides, max over ranks.  ys (1 GB) > L2 (126 MB).
+  e2e     the public API `moment_filter_rms(...)` with HOST buffers (pinned), H2D of ys, kernel, D2H of the full
+          history inside the timed region, on an --e2e-batch slice of the same workload (the 128 GB/step history of
+          the full batch does not fit pinned host memory); plus `e2e_nell_only` on the full batch.
+  roofline  FP64 FMA pipe (the path is compute-bound: ~53 flop/B): algorithmic flops W(8)=6851 per filter-step
+           / kernel time, against the FP64 FMA peak measured live by mfs_fp64_peak (MEASURED_PEAKS.json
+          holds no FP64 figure).  `hbm` sub-object gives the secondary HBM figure against MEASURED_PEAKS.json.
+  cpu_baseline  oracle/libmfs_oracle.so (C restatement of the reference's dense algorithm, pthreads over filters) on a
+          bounded sample, all host cores.  The JAX reference itself cannot run here (no jax / tme, no network).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'benes_bernoulli_filter_steps_per_s'
+UNIT = 'filter-steps/s'
+
+
+def work_per_step(N: int) -> float:
+    """Algorithmic FP64 flop per filter-step, SURVEY.md 8(d): W(N) = 2/3 N^3 + 85 N^2 + 130 N + 30."""
+    return 2. / 3. * N ** 3 + 85. * N ** 2 + 130. * N + 30.
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                              ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(mx)] if sm else []
+        return {'sm_mhz': float(np.median(busy or sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_baseline(N, T, target_seconds=15., threads=0, seed=666 + 1):
+    """Time the C oracle on a bounded sample of the same workload.  Returns (steps/s, cores, sample string)."""
+    from oracle import c_oracle
+    from mfs_b200.one_dim.moments import sde_cond_moments_tme
+    from mfs_b200.one_dim.ss_models import benes_bernoulli
+    from mfs_b200.synthetic import benes_bernoulli_ys_numpy
+    dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
+    fam = sde_cond_moments_tme(drift, disp, dt, 3)
+    cores = c_oracle.max_threads() if threads <= 0 else threads
+    probe_b = 16 * cores
+    ys = benes_bernoulli_ys_numpy(probe_b, T, seed)
+    t0 = time.perf_counter()
+    c_oracle.filter_1d('raw', fam[0], pmf, ic.rms, ys, history='full', num_threads=cores)
+    rate = probe_b * T / (time.perf_counter() - t0)
+    b = int(max(probe_b, min(262144, rate * target_seconds / T)) // (16 * cores) * (16 * cores))
+    ys = benes_bernoulli_ys_numpy(b, T, seed + 1)
+    t0 = time.perf_counter()
+    out = c_oracle.filter_1d('raw', fam[0], pmf, ic.rms, ys, history='full', num_threads=cores)
+    el = time.perf_counter() - t0
+    return b * T / el, int(out['threads']), f'{b} filters x T={T} (first {b} of the seeded workload), full history, {el:.1f} s', b
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  The JAX reference cannot be installed or run
+    in this image (jax, jaxlib, tme absent; no network), so this arm times the C restatement of its algorithm
+    (oracle/mfs_oracle.c) with all host threads -- rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    N, T = args.N, args.T
+    from oracle import c_oracle
+    from mfs_b200.one_dim.moments import sde_cond_moments_tme
+    from mfs_b200.one_dim.ss_models import benes_bernoulli
+    from mfs_b200.synthetic import benes_bernoulli_ys_numpy
+    dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
+    fam = sde_cond_moments_tme(drift, disp, dt, 3)
+    cores = c_oracle.max_threads()
+    # size one step for ~ref_step_seconds of CPU work
+    probe_b = 16 * cores
+    ys = benes_bernoulli_ys_numpy(probe_b, T, 667)
+    t0 = time.perf_counter()
+    c_oracle.filter_1d('raw', fam[0], pmf, ic.rms, ys, history='full', num_threads=cores)
+    rate = probe_b * T / (time.perf_counter() - t0)
+    b = int(max(probe_b, rate * args.ref_step_seconds / T) // (16 * cores) * (16 * cores))
+    ys = benes_bernoulli_ys_numpy(b, T, 668)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = c_oracle.filter_1d('raw', fam[0], pmf, ic.rms, ys, history='full', num_threads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = args.steps * b * T / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'Benes-Bernoulli 1D raw-moment filter, TME-3 transition, N={N}, T={T}, '
+                               f'bounded sample of {b} filters per step (full workload: {args.batch} per GPU)',
+                   'N': N, 'T': T, 'batch_per_step': b, 'mode': 'raw', 'history': 'full'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': int(out['threads']), 'kind': 'port',
+                         'sample': f'{b} filters x T={T} per step, {args.steps} steps; C restatement of the reference '
+                                   f'algorithm (dense Cholesky + trsm + symmetric eigensolver), not JAX'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'diverged_frac': float(np.mean(out['status'] >= 0)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='mfs_b200', choices=['mfs_b200', 'reference'])
+    ap.add_argument('--N', type=int, default=8)
+    ap.add_argument('--T', type=int, default=1000)
+    ap.add_argument('--batch', type=int, default=1_000_000, help='filters per GPU')
+    ap.add_argument('--mode', default='raw', choices=['raw', 'central'])
+    ap.add_argument('--history', default='full', choices=['full', 'last', 'none'])
+    ap.add_argument('--e2e-batch', type=int, default=131072, help='filters per GPU in the host-buffer (e2e) leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--ref-step-seconds', type=float, default=10.)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mfs_b200
+    from mfs_b200 import _lib
+    from mfs_b200.one_dim.filtering import moment_filter_rms, moment_filter_cms
+    from mfs_b200.one_dim.moments import sde_cond_moments_tme
+    from mfs_b200.one_dim.ss_models import benes_bernoulli
+    from mfs_b200.synthetic import benes_bernoulli_ys_torch
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    N, T, B = args.N, args.T, args.batch
+    M = 2 * N
+    dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
+    fam = sde_cond_moments_tme(drift, disp, dt, 3)
+
+    # the seeded synthetic workload of this rank's shard (weak scaling: B filters per GPU), resident in HBM
+    ys = benes_bernoulli_ys_torch(B, T, 666 + 1 + 1000 * rank, dev)
+    out_bufs = {'nell': torch.empty(B, dtype=torch.float64, device=dev),
+                'status': torch.empty(B, dtype=torch.int32, device=dev)}
+    if args.history == 'full':
+        out_bufs['ms'] = torch.empty((B, T, M), dtype=torch.float64, device=dev)
+        if args.mode == 'central':
+            out_bufs['mean'] = torch.empty((B, T), dtype=torch.float64, device=dev)
+    elif args.history == 'last':
+        out_bufs['ms'] = torch.empty((B, M), dtype=torch.float64, device=dev)
+        if args.mode == 'central':
+            out_bufs['mean'] = torch.empty((B,), dtype=torch.float64, device=dev)
+
+    def step(ys_in, bufs, history):
+        if args.mode == 'raw':
+            return moment_filter_rms(fam[0], pmf, ic.rms, ys_in, history=history, return_status=True, out=bufs)
+        return moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys_in, history=history, return_status=True,
+                                 out=bufs)
+
+    fp64_peak, _ = mfs_b200.fp64_peak(local_rank, 4096)      # roofline denominator, measured on this GPU
+    for _ in range(args.warmup):
+        step(ys, out_bufs, args.history)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record()
+        res = step(ys, out_bufs, args.history)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    status = res[-1]
+    diverged = float((status >= 0).double().mean().item())
+    live = float(torch.where(status >= 0, status, torch.full_like(status, T)).double().sum().item()) / (B * T)
+
+    tmax = torch.tensor([total_ms, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    agg = torch.tensor([diverged, live, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, kernel_ms_avg = float(tmax[0]), float(tmax[1])
+    diverged, live, launches_all = float(agg[0]) / world, float(agg[1]) / world, int(agg[2])
+    steps_per_launch = B * T
+    value = world * args.steps * steps_per_launch / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API (H2D + kernel + D2H every step) ----
+    e2e = None
+    e2e_nell = None
+    if not args.no_e2e:
+        Be = min(args.e2e_batch, B)
+        ys_host = torch.empty((Be, T), dtype=torch.uint8).pin_memory()
+        ys_host.copy_(ys[:Be])
+        hist_bufs = {'ms': torch.empty((Be, T, M), dtype=torch.float64).pin_memory(),
+                     'nell': torch.empty(Be, dtype=torch.float64).pin_memory(),
+                     'status': torch.empty(Be, dtype=torch.int32).pin_memory()}
+        if args.mode == 'central':
+            hist_bufs['mean'] = torch.empty((Be, T), dtype=torch.float64).pin_memory()
+
+        def host_step(ys_np, bufs, history):
+            if args.mode == 'raw':
+                return moment_filter_rms(fam[0], pmf, ic.rms, ys_np, history=history, device=local_rank,
+                                         return_status=True, out=bufs)
+            return moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys_np, history=history, device=local_rank,
+                                     return_status=True, out=bufs)
+
+        ys_np = ys_host.numpy()
+        host_step(ys_np, hist_bufs, 'full')
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step(ys_np, hist_bufs, 'full')      # returns after the last D2H completed
+        barrier()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = Be * T + 8 * (M + 8)
+        d2h = Be * T * M * 8 + Be * 12 + (Be * T * 8 if args.mode == 'central' else 0)
+        e2e = {'value': world * args.steps * Be * T / float(tt[0]), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'batch_per_gpu': Be, 'history': 'full',
+               'note': 'pinned host buffers, chunked H2D->kernel->D2H pipeline inside mfs_filter_1d_host'}
+        del hist_bufs
+
+        # nell-only objective (parameter-estimation use): whole batch from host memory
+        ys_full = torch.empty((B, T), dtype=torch.uint8).pin_memory()
+        ys_full.copy_(ys)
+        nbufs = {'nell': torch.empty(B, dtype=torch.float64).pin_memory(),
+                 'status': torch.empty(B, dtype=torch.int32).pin_memory()}
+        host_step(ys_full.numpy(), nbufs, 'none')
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step(ys_full.numpy(), nbufs, 'none')
+        barrier()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_nell = {'value': world * args.steps * B * T / float(tt[0]), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(B * T), 'd2h_bytes_per_step': int(B * 12), 'history': 'none'}
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        W = work_per_step(N)
+        achieved_tf = W * steps_per_launch / (kernel_ms_avg * 1e-3) / 1e12
+        alg_bytes = (1 + (8 * M if args.history == 'full' else 0)) * steps_per_launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+                tj = json.load(f)
+            key = f'N{N}_T{T}_B{B}_{args.mode}_{args.history}'
+            traffic = tj.get(key)
+        except Exception:
+            pass
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'BASELINE configs[1]: Benes-Bernoulli 1D {args.mode}-moment filter, TME-3 '
+                                   f'transition, N={N} nodes ({M} moments), T={T}, {B} independent filters per GPU',
+                       'N': N, 'T': T, 'batch_per_gpu': B, 'global_batch': B * world, 'mode': args.mode,
+                       'history': args.history, 'sharding': f'batch axis over {world} rank(s), no data-path collective',
+                       'l2': 'inputs_larger_than_l2 (ys 1 GB, outputs 128 GB per step)', 'seed': 667},
+            'roofline': {'bound': 'fp64_fma', 'achieved': achieved_tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
+                         'frac': achieved_tf / (fp64_peak / 1e12), 'traffic': traffic,
+                         'peak_source': 'measured live: mfs_fp64_peak DFMA micro-benchmark on this GPU '
+                                        '(MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)',
+                         'flop_per_filter_step': W, 'kernel_ms': kernel_ms_avg,
+                         'hbm': {'achieved': alg_bytes / (kernel_ms_avg * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                                 'unit': 'GB/s', 'peak_source': peaks_src,
+                                 'frac': alg_bytes / (kernel_ms_avg * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                 'algorithmic_bytes_per_launch': alg_bytes}},
+            'clocks': clocks, 'gpu_launches': launches_all, 'e2e': e2e, 'e2e_nell_only': e2e_nell,
+            'diverged_frac': diverged, 'live_step_frac': live, 'wall_s_timed_region': t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, sample, _ = cpu_baseline(N, T)
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': sample + '; C restatement of the reference algorithm, not JAX'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -6,6 +6,9 @@
 namespace mfs {
 
 constexpr int kBlock = 128;
+#ifndef MFS_MIN_BLOCKS
+#define MFS_MIN_BLOCKS 3   // CTAs per SM the register allocation must allow (tuned on B200)
+#endif
 
 // Transition kinds the kernel is specialised on (compile time); drift / order / family are runtime switches inside.
 enum { KIND_TME = 0, KIND_NORMAL = 1, KIND_BENES_TME = 2 };
@@ -44,7 +47,7 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
   // pass 1: predicted mean (and scale) -- filtering.py:146-147, :223-224
   if (KIND == KIND_BENES_TME) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) tn[i] = tanh(x[i]);
+    for (int i = 0; i < N; ++i) tn[i] = tanh_fast(x[i]);
   }
   if (MODE != MFS_MODE_RAW) {
     double m_acc = 0.0, v_acc = 0.0;
@@ -168,9 +171,12 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
                       const double (&x)[N], double (&ms)[2 * N], double& mean, double& scale) {
   double u[N];
   double cc = 0.0;
+  MeasStep st;
+  st.y = y;
+  st.c0 = (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) ? 0.0 : meas_step_constant(P.meas_id, y, mprm[1]);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    u[i] = w[i] * measurement_pdf(P.meas_id, y, x[i], mprm);
+    u[i] = w[i] * measurement_pdf(P.meas_id, st, x[i], mprm);
     cc += u[i];
   }
   const double cinv = 1.0 / cc;
@@ -207,7 +213,7 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND>
-__global__ void __launch_bounds__(kBlock) filter1d_kernel(const mfs_filter1d_args P) {
+__global__ void __launch_bounds__(kBlock, MFS_MIN_BLOCKS) filter1d_kernel(const mfs_filter1d_args P) {
   const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (b >= P.B) return;
 
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(kBlock) filter1d_kernel(const mfs_filter1d_arg
   double tp[MFS_MAX_PARAMS], mp[MFS_MAX_PARAMS];
 #pragma unroll
   for (int k = 0; k < MFS_MAX_PARAMS; ++k) { tp[k] = __ldg(tprm + k); mp[k] = __ldg(mprm + k); }
+  if (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) mp[2] = 1.0 / mp[0];
 
   const int64_t ys_off = b * P.ys_stride_b;
   double* ms_out = P.ms_out ? P.ms_out + b * P.ms_stride_b : nullptr;
@@ -236,15 +243,21 @@ __global__ void __launch_bounds__(kBlock) filter1d_kernel(const mfs_filter1d_arg
     const double y = y_next;
     if (t + 1 < P.T) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
 
-    double w[N], x[N];
-    bool ok = moment_quadrature<N>(ms, mean, scale, w, x);
-    if (ok) {
-      predict<N, MODE, KIND>(P, tp, w, x, ms, mean, scale);
+    // two half-steps sharing ONE instance of the quadrature code: phase 0 = prediction, phase 1 = update
+    bool ok = true;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      double w[N], x[N];
       ok = moment_quadrature<N>(ms, mean, scale, w, x);
+      if (!ok) break;
+      if (phase == 0) {
+        predict<N, MODE, KIND>(P, tp, w, x, ms, mean, scale);
+      } else {
+        const double cc = update<N, MODE>(P, mp, y, w, x, ms, mean, scale);
+        nell -= log(cc);
+      }
     }
     if (!ok) { status = (int)t; break; }
-    const double cc = update<N, MODE>(P, mp, y, w, x, ms, mean, scale);
-    nell -= log(cc);
 
     if (P.out_mode == MFS_OUT_FULL) {
       double* o = ms_out + t * P.ms_stride_t;

@@ -13,11 +13,18 @@ namespace mfs {
 
 struct Jet { double a0, a1, a2, a3, a4; };  // a, a', a'', a''', a''''
 
+// tanh through one exp and one reciprocal: 1 - 2/(1 + e^{2x}).  Absolute error ~1e-16 (relative accuracy degrades
+// only for |x| << 1, where tanh enters the transition moments multiplied by dt and added to O(1) terms).  The
+// exponent is clamped so that e^{2x} stays finite (rcp_fast(inf) would be NaN); tanh is 1 to the last bit there.
+MFS_DEV double tanh_fast(double x) {
+  return fma(-2.0, rcp_fast(1.0 + exp(fmin(2.0 * x, 708.0))), 1.0);
+}
+
 // mfs/one_dim/ss_models.py:37 (tanh), :71 (x(1-theta1 x^2)); tests/test_filtering.py:45 (-x/ell as a*x)
 MFS_DEV Jet drift_jet(int drift_id, double x, const double* prm) {
   Jet j;
   if (drift_id == MFS_DRIFT_BENES) {
-    const double t = tanh(x);
+    const double t = tanh_fast(x);
     const double u = fma(-t, t, 1.0);
     j.a0 = t;
     j.a1 = u;
@@ -129,20 +136,35 @@ MFS_DEV void normal_mean_var(int trans_id, int drift_id, int order, double x, do
 }
 
 // p(y | x): mfs/one_dim/ss_models.py:43-47, :80-84; tests/test_filtering.py:41-42; mfs/multi_dims/ss_models.py:63-67
-MFS_DEV double measurement_pdf(int meas_id, double y, double x, const double* prm) {
-  if (meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
-    const double zz = x * x * x / prm[0] - prm[1];
-    const double p = 1.0 / (1.0 + exp(-zz));
-    return (y != 0.0) ? p : 1.0 - p;
-  } else if (meas_id == MFS_MEAS_POISSON_SOFTPLUS) {
-    const double mu = log(1.0 + exp(prm[0] * x));
+// Per-step, node-independent part (computed once per measurement).
+struct MeasStep { double y; double c0; };
+
+static __device__ __noinline__ double meas_step_constant(int meas_id, double y, double r) {
+  if (meas_id == MFS_MEAS_POISSON_SOFTPLUS) return lgamma(y + 1.0);
+  if (meas_id == MFS_MEAS_GAUSSIAN) return 1.0 / (r * 2.5066282746310002);
+  return 0.0;
+}
+
+// The models that are not on the headline path live out of line: one copy of their exp/log code, not one per node.
+static __device__ __noinline__ double measurement_pdf_generic(int meas_id, double y, double c0, double x, double p0,
+                                                       double p1) {
+  if (meas_id == MFS_MEAS_POISSON_SOFTPLUS) {
+    const double mu = log(1.0 + exp(p0 * x));
     const double klogmu = (y == 0.0) ? 0.0 : y * log(mu);   // xlogy
-    return exp(klogmu - lgamma(y + 1.0) - mu);
-  } else {  // MFS_MEAS_GAUSSIAN
-    const double r = prm[1];
-    const double zz = (y - prm[0] * x) / r;
-    return exp(-0.5 * zz * zz) / (r * 2.5066282746310002);
+    return exp(klogmu - c0 - mu);
   }
+  // MFS_MEAS_GAUSSIAN
+  const double zz = (y - p0 * x) / p1;
+  return exp(-0.5 * zz * zz) * c0;
+}
+
+MFS_DEV double measurement_pdf(int meas_id, const MeasStep& st, double x, const double* prm) {
+  if (meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
+    const double zz = fma(x * x, x * prm[2], -prm[1]);      // prm[2] = 1/c0, filled in by the kernel prologue
+    const double p = rcp_fast(1.0 + exp(fmin(-zz, 708.0)));   // 1/(1+inf) = 0 in the reference; 3e-308 here
+    return (st.y != 0.0) ? p : 1.0 - p;
+  }
+  return measurement_pdf_generic(meas_id, st.y, st.c0, x, prm[0], prm[1]);
 }
 
 template <int P>

@@ -50,7 +50,7 @@ def _ys_dtype_code(dtype_name: str) -> int:
 
 
 def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stable: bool, history: str,
-         device: Optional[int], return_status: bool, chunk_filters: int):
+         device: Optional[int], return_status: bool, chunk_filters: int, out: Optional[dict] = None):
     if history not in _lib.OUT_MODE:
         raise ValueError(f"history must be one of {sorted(_lib.OUT_MODE)}")
     on_device = _is_torch_cuda(ys)
@@ -131,24 +131,34 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
         if scale0_tab is not None:
             a.scale0 = to_dev(scale0_tab)
         f64 = dict(dtype=torch.float64, device=dev)
-        nell = torch.empty(B, **f64)
-        status = torch.empty(B, dtype=torch.int32, device=dev)
+        out = out or {}
+
+        def alloc(key, shape, dtype=torch.float64):
+            t = out.get(key)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            if not (t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.numel() == int(np.prod(shape))):
+                raise ValueError(f"out[{key!r}] must be a contiguous {dtype} CUDA tensor with {int(np.prod(shape))} elements")
+            return t.view(shape)
+
+        nell = alloc('nell', (B,))
+        status = alloc('status', (B,), torch.int32)
         ms_out = mean_out = scale_out = None
         if history == 'full':
-            ms_out = torch.empty((B, T, M), **f64)
+            ms_out = alloc('ms', (B, T, M))
             a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = T * M, M, T
             aux_shape = (B, T)
         elif history == 'last':
-            ms_out = torch.empty((B, M), **f64)
+            ms_out = alloc('ms', (B, M))
             a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = M, 0, 1
             aux_shape = (B,)
         if ms_out is not None:
             a.ms_out = ms_out.data_ptr()
             if mode != 'raw':
-                mean_out = torch.empty(aux_shape, **f64)
+                mean_out = alloc('mean', aux_shape)
                 a.mean_out = mean_out.data_ptr()
             if mode == 'scaled':
-                scale_out = torch.empty(aux_shape, **f64)
+                scale_out = alloc('scale', aux_shape)
                 a.scale_out = scale_out.data_ptr()
         a.nell_out, a.status_out = nell.data_ptr(), status.data_ptr()
         with torch.cuda.device(dev):
@@ -167,24 +177,36 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
             a.mean0 = ptr(mean0_tab)
         if scale0_tab is not None:
             a.scale0 = ptr(scale0_tab)
-        nell = np.empty(B, dtype=np.float64)
-        status = np.empty(B, dtype=np.int32)
+        out = out or {}
+
+        def alloc(key, shape, dtype=np.float64):
+            arr = out.get(key)
+            if arr is None:
+                return np.empty(shape, dtype=dtype)
+            if type(arr).__module__.startswith('torch'):
+                arr = arr.numpy()       # e.g. a pinned CPU tensor: zero-copy view
+            if not (arr.dtype == dtype and arr.flags['C_CONTIGUOUS'] and arr.size == int(np.prod(shape))):
+                raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array with {int(np.prod(shape))} elements")
+            return arr.reshape(shape)
+
+        nell = alloc('nell', (B,))
+        status = alloc('status', (B,), np.int32)
         ms_out = mean_out = scale_out = None
         if history == 'full':
-            ms_out = np.empty((B, T, M), dtype=np.float64)
+            ms_out = alloc('ms', (B, T, M))
             a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = T * M, M, T
             aux_shape = (B, T)
         elif history == 'last':
-            ms_out = np.empty((B, M), dtype=np.float64)
+            ms_out = alloc('ms', (B, M))
             a.ms_stride_b, a.ms_stride_t, a.aux_stride_b = M, 0, 1
             aux_shape = (B,)
         if ms_out is not None:
             a.ms_out = ptr(ms_out)
             if mode != 'raw':
-                mean_out = np.empty(aux_shape, dtype=np.float64)
+                mean_out = alloc('mean', aux_shape)
                 a.mean_out = ptr(mean_out)
             if mode == 'scaled':
-                scale_out = np.empty(aux_shape, dtype=np.float64)
+                scale_out = alloc('scale', aux_shape)
                 a.scale_out = ptr(scale_out)
         a.nell_out, a.status_out = ptr(nell), ptr(status)
         if device is None:
@@ -206,38 +228,39 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
 
 def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, stable: bool = False, *,
                       history: str = 'full', device: Optional[int] = None, return_status: bool = False,
-                      chunk_filters: int = 0):
+                      chunk_filters: int = 0, out: Optional[dict] = None):
     """Raw-moment filter, mirror of ``mfs/one_dim/filtering.py:32-89``.
 
     Returns ``(rmss (..., T, 2N), nell (...))`` like the reference (``history='last'`` -> ``(..., 2N)``,
     ``'none'`` -> ``None``); with ``return_status=True`` a third element holds the first failed step per filter
     (-1: none).  A filter whose moment matrix stops being positive definite yields NaN from that step on, exactly like
-    the JAX scan.
+    the JAX scan.  ``out`` may hold preallocated result buffers under the keys 'ms', 'mean', 'scale', 'nell', 'status'
+    (CUDA tensors on the device path; NumPy arrays or pinned CPU tensors on the host path) to avoid re-allocation.
     """
     fn = _check_transition(state_cond_raw_moments, 'raw', 'state_cond_raw_moments')
     out = _run('raw', fn.spec, _check_measurement(measurement_cond_pdf), rms0, None, None, ys, stable, history,
-               device, return_status, chunk_filters)
+               device, return_status, chunk_filters, out)
     res = (out['ms'], out['nell'])
     return res + (out['status'],) if return_status else res
 
 
 def moment_filter_cms(state_cond_central_moments, state_cond_mean, measurement_cond_pdf, cms0, mean0, ys,
                       stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
-                      return_status: bool = False, chunk_filters: int = 0):
+                      return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None):
     """Central-moment filter, mirror of ``mfs/one_dim/filtering.py:92-161``.  Returns ``(cmss, means, nell)``."""
     fn = _check_transition(state_cond_central_moments, 'central', 'state_cond_central_moments')
     fm = _check_transition(state_cond_mean, 'mean', 'state_cond_mean')
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_central_moments and state_cond_mean must come from the same factory call')
     out = _run('central', fn.spec, _check_measurement(measurement_cond_pdf), cms0, mean0, None, ys, stable, history,
-               device, return_status, chunk_filters)
+               device, return_status, chunk_filters, out)
     res = (out['ms'], out['mean'], out['nell'])
     return res + (out['status'],) if return_status else res
 
 
 def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, measurement_cond_pdf, scms0, mean0,
                        scale0, ys, stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
-                       return_status: bool = False, chunk_filters: int = 0):
+                       return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None):
     """Scaled-central-moment filter, mirror of ``mfs/one_dim/filtering.py:164-240``.
     Returns ``(scmss, means, scales, nell)``."""
     fn = _check_transition(state_cond_scaled_central_moments, 'scaled', 'state_cond_scaled_central_moments')
@@ -245,6 +268,6 @@ def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, m
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_scaled_central_moments and state_cond_mean_var must come from the same factory')
     out = _run('scaled', fn.spec, _check_measurement(measurement_cond_pdf), scms0, mean0, scale0, ys, stable,
-               history, device, return_status, chunk_filters)
+               history, device, return_status, chunk_filters, out)
     res = (out['ms'], out['mean'], out['scale'], out['nell'])
     return res + (out['status'],) if return_status else res

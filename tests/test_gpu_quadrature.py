@@ -1,0 +1,59 @@
+"""Batched moment_quadrature on the GPU vs the reference-generated golden vectors and the reference's own
+known-answer tests (tests/test_one_dim_quadrature.py)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from mfs_b200.one_dim.quadtures import moment_quadrature  # noqa: E402
+from mfs_b200.one_dim.moments import raw_moment_of_normal, raw_to_central, raw_to_scaled  # noqa: E402
+from mfs_b200 import _lib  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_against_reference_golden():
+    g = np.load(os.path.join(GOLD, 'golden_quadrature_1d.npz'))
+    names = sorted({k.split('/')[0] for k in g.files if k.split('/')[0] != 'nonpd'})
+    for name in names:
+        ms, mean, scale = g[f'{name}/ms'], float(g[f'{name}/mean']), float(g[f'{name}/scale'])
+        w, x = moment_quadrature(ms, mean, scale, sort_nodes=True)
+        n = len(ms) // 2
+        tol = 1e-13 * 10 ** max(0, n - 3)
+        np.testing.assert_allclose(x, g[f'{name}/nodes'], rtol=tol, atol=tol)
+        np.testing.assert_allclose(w, g[f'{name}/weights'], rtol=max(tol, 1e-12) * 100, atol=tol)
+        assert abs(w.sum() - 1) < 1e-12
+    w, x = moment_quadrature(g['nonpd/ms'])
+    assert np.all(np.isnan(w)) and np.all(np.isnan(x))
+
+
+def test_reference_known_answers_batched():
+    m, v, n = 0.2, 1.1, 8
+    rms = np.array([raw_moment_of_normal(m, v, p) for p in range(2 * n)])
+    ms = torch.from_numpy(np.stack([rms, raw_to_central(rms), raw_to_scaled(rms)])).cuda()
+    mean = torch.tensor([0., m, m], dtype=torch.float64, device='cuda')
+    scale = torch.tensor([1., 1., math.sqrt(v)], dtype=torch.float64, device='cuda')
+    w, x = moment_quadrature(ms, mean, scale, sort_nodes=True)
+    assert w.is_cuda and w.shape == (3, n)
+    w, x = w.cpu().numpy(), x.cpu().numpy()
+    for k in range(3):
+        np.testing.assert_array_almost_equal(w[k], w[0], decimal=6)
+        np.testing.assert_array_almost_equal(x[k], x[0], decimal=6)
+        np.testing.assert_allclose(np.dot(w[k], np.exp(x[k])), math.exp(m + v / 2), rtol=1e-7)
+        np.testing.assert_allclose(np.dot(w[k], np.sin(x[k])), math.exp(-v / 2) * math.sin(m), rtol=1e-6)
+        np.testing.assert_allclose(np.dot(w[k], np.exp(-(x[k] - 2) ** 2 / 6) / math.sqrt(6 * math.pi)),
+                                   math.exp(-(2 - m) ** 2 / (2 * (v + 3))) / math.sqrt(2 * math.pi * (v + 3)), rtol=1e-6)
+        for p in range(2 * n):
+            np.testing.assert_allclose(np.dot(w[k], x[k] ** p), rms[p], rtol=1e-7, atol=1e-9)
+    a, b = -2., 3.
+    for nn in (1, 2, 3, 4):
+        mu = np.array([(b ** (p + 1) - a ** (p + 1)) / ((p + 1) * (b - a)) for p in range(2 * nn)])
+        w, x = moment_quadrature(mu)
+        for p in range(2 * nn):
+            np.testing.assert_allclose(np.dot(w, x ** p), mu[p], rtol=1e-7)
+    with pytest.raises(_lib.MfsError):
+        moment_quadrature(rms, ldl=True)
