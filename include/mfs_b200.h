@@ -69,6 +69,14 @@ enum {
   MFS_OUT_NONE = 2  /* only nell (parameter-estimation objective, dardel/parameter_estimation/mf.py:52)       */
 };
 
+/* flags.
+ * By default the prediction half-step does not re-derive its quadrature from the posterior moments: the posterior of
+ * the previous update IS an N-atom measure {x_i, w_i l_i / c}, whose N-point Gauss rule is itself, so the atoms are
+ * carried over (the Hankel pivots are still checked on the moments, so "matrix not positive definite -> NaN" fires on
+ * the same quantity as the reference's Cholesky).  MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE forces the literal recursion
+ * of mfs/one_dim/filtering.py:78 (a second moment_quadrature per step), which agrees to rounding. */
+#define MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE 1
+
 typedef struct mfs_filter1d_args {
   int32_t abi_version;   /* MFS_ABI_VERSION */
   int32_t mode;          /* MFS_MODE_*  */
@@ -109,6 +117,8 @@ typedef struct mfs_filter1d_args {
   int64_t aux_stride_b;
   double* nell_out;      /* [B] negative log-likelihood */
   int32_t* status_out;   /* [B] first failed step or -1; may be NULL */
+  int32_t flags;         /* MFS_FLAG_* */
+  int32_t reserved0;
 } mfs_filter1d_args;
 
 /* ABI version of the loaded library. */

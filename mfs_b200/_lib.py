@@ -21,6 +21,7 @@ DRIFT = {'benes': 0, 'well': 1, 'linear': 2}
 MEAS = {'bernoulli_logistic_cubic': 0, 'poisson_softplus': 1, 'gaussian': 2}
 YS_DTYPE = {'uint8': 0, 'bool': 0, 'int32': 1, 'float64': 2}
 OUT_MODE = {'full': 0, 'last': 1, 'none': 2}
+FLAG_RECOMPUTE_PREDICT_QUADRATURE = 1
 
 
 class Filter1dArgs(ctypes.Structure):
@@ -41,6 +42,7 @@ class Filter1dArgs(ctypes.Structure):
         ('ms_out', ctypes.c_void_p), ('ms_stride_b', ctypes.c_int64), ('ms_stride_t', ctypes.c_int64),
         ('mean_out', ctypes.c_void_p), ('scale_out', ctypes.c_void_p), ('aux_stride_b', ctypes.c_int64),
         ('nell_out', ctypes.c_void_p), ('status_out', ctypes.c_void_p),
+        ('flags', ctypes.c_int32), ('reserved0', ctypes.c_int32),
     ]
 
 

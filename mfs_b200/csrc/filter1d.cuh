@@ -6,8 +6,14 @@
 namespace mfs {
 
 constexpr int kBlock = 128;
-#ifndef MFS_MIN_BLOCKS
-#define MFS_MIN_BLOCKS 3   // CTAs per SM the register allocation must allow (tuned on B200)
+
+// CTAs of 128 threads per SM that the register allocation must allow.  The step is a long dependent FP64 chain (QL
+// rotations), so resident warps are what hides the DFMA latency; measured on B200 (profiles/r1_occupancy_sweep.md):
+// N=5 fastest at 6 CTAs/SM (<=80 regs), N=8 at 4 (<=128 regs, spills beyond), N=12 at 3 (<=168 regs).
+#ifdef MFS_MIN_BLOCKS
+template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
+#else
+template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
 #endif
 
 // Transition kinds the kernel is specialised on (compile time); drift / order / family are runtime switches inside.
@@ -167,7 +173,7 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
 // Update: ms <- sum_i w_i delta_i^p l_i / c ; returns c = sum_i w_i l_i   (filtering.py:82-85, :151-157, :228-236)
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE>
-MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, const double (&w)[N],
+MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, double (&w)[N],
                       const double (&x)[N], double (&ms)[2 * N], double& mean, double& scale) {
   double u[N];
   double cc = 0.0;
@@ -208,12 +214,15 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   }
 #pragma unroll
   for (int p = 0; p < 2 * N; ++p) ms[p] *= cinv;
+  // the posterior is the N-atom measure {x_i, u_i / c}: its weights replace the prior ones (see MFS_FLAG_* in the header)
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = u[i] * cinv;
   return cc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND>
-__global__ void __launch_bounds__(kBlock, MFS_MIN_BLOCKS) filter1d_kernel(const mfs_filter1d_args P) {
+__global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P) {
   const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (b >= P.B) return;
 
@@ -237,24 +246,28 @@ __global__ void __launch_bounds__(kBlock, MFS_MIN_BLOCKS) filter1d_kernel(const 
 
   double nell = 0.0;
   int status = -1;
+  double w[N], x[N];          // quadrature of the current half-step; carried across steps as the posterior atoms
+  bool have_atoms = false;
   double y_next = load_y(P.ys, P.ys_dtype, ys_off);
   int64_t t = 0;
   for (; t < P.T; ++t) {
     const double y = y_next;
     if (t + 1 < P.T) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
 
-    // two half-steps sharing ONE instance of the quadrature code: phase 0 = prediction, phase 1 = update
+    // two half-steps sharing ONE instance of the quadrature code: phase 0 = prediction, phase 1 = update.
+    // From the second step on, phase 0 re-uses the atoms (x_i, w_i l_i / c) of the previous update as its quadrature.
     bool ok = true;
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
-      double w[N], x[N];
-      ok = moment_quadrature<N>(ms, mean, scale, w, x);
+      if (phase == 0 && have_atoms) ok = hankel_is_pd<N>(ms);
+      else ok = moment_quadrature<N>(ms, mean, scale, w, x);
       if (!ok) break;
       if (phase == 0) {
         predict<N, MODE, KIND>(P, tp, w, x, ms, mean, scale);
       } else {
         const double cc = update<N, MODE>(P, mp, y, w, x, ms, mean, scale);
         nell -= log(cc);
+        have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE);
       }
     }
     if (!ok) { status = (int)t; break; }

@@ -50,7 +50,8 @@ def _ys_dtype_code(dtype_name: str) -> int:
 
 
 def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stable: bool, history: str,
-         device: Optional[int], return_status: bool, chunk_filters: int, out: Optional[dict] = None):
+         device: Optional[int], return_status: bool, chunk_filters: int, out: Optional[dict] = None,
+         recompute_predict_quadrature: bool = False):
     if history not in _lib.OUT_MODE:
         raise ValueError(f"history must be one of {sorted(_lib.OUT_MODE)}")
     on_device = _is_torch_cuda(ys)
@@ -106,6 +107,7 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
     a.trans_param_stride, a.meas_param_stride = tstride, mstride
     a.ms0_stride, a.mean0_stride, a.scale0_stride = ms0_stride, mean0_stride, scale0_stride
     a.out_mode = _lib.OUT_MODE[history]
+    a.flags = _lib.FLAG_RECOMPUTE_PREDICT_QUADRATURE if recompute_predict_quadrature else 0
     a.ys_stride_b, a.ys_stride_t = T, 1
 
     L = _lib.lib()
@@ -228,7 +230,8 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
 
 def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, stable: bool = False, *,
                       history: str = 'full', device: Optional[int] = None, return_status: bool = False,
-                      chunk_filters: int = 0, out: Optional[dict] = None):
+                      chunk_filters: int = 0, out: Optional[dict] = None,
+                      recompute_predict_quadrature: bool = False):
     """Raw-moment filter, mirror of ``mfs/one_dim/filtering.py:32-89``.
 
     Returns ``(rmss (..., T, 2N), nell (...))`` like the reference (``history='last'`` -> ``(..., 2N)``,
@@ -236,31 +239,38 @@ def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, st
     (-1: none).  A filter whose moment matrix stops being positive definite yields NaN from that step on, exactly like
     the JAX scan.  ``out`` may hold preallocated result buffers under the keys 'ms', 'mean', 'scale', 'nell', 'status'
     (CUDA tensors on the device path; NumPy arrays or pinned CPU tensors on the host path) to avoid re-allocation.
+
+    ``recompute_predict_quadrature=True`` forces the literal recursion of the reference (a second ``moment_quadrature``
+    per step, ``filtering.py:78``).  By default the prediction half-step re-uses the posterior atoms
+    ``{x_i, w_i p(y|x_i)/c}`` of the previous update -- the N-point Gauss rule of an N-atom measure is the measure
+    itself -- while still testing the Hankel pivots of the posterior moments, so NaN-on-non-PD fires identically.
     """
     fn = _check_transition(state_cond_raw_moments, 'raw', 'state_cond_raw_moments')
     out = _run('raw', fn.spec, _check_measurement(measurement_cond_pdf), rms0, None, None, ys, stable, history,
-               device, return_status, chunk_filters, out)
+               device, return_status, chunk_filters, out, recompute_predict_quadrature)
     res = (out['ms'], out['nell'])
     return res + (out['status'],) if return_status else res
 
 
 def moment_filter_cms(state_cond_central_moments, state_cond_mean, measurement_cond_pdf, cms0, mean0, ys,
                       stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
-                      return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None):
+                      return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None,
+                      recompute_predict_quadrature: bool = False):
     """Central-moment filter, mirror of ``mfs/one_dim/filtering.py:92-161``.  Returns ``(cmss, means, nell)``."""
     fn = _check_transition(state_cond_central_moments, 'central', 'state_cond_central_moments')
     fm = _check_transition(state_cond_mean, 'mean', 'state_cond_mean')
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_central_moments and state_cond_mean must come from the same factory call')
     out = _run('central', fn.spec, _check_measurement(measurement_cond_pdf), cms0, mean0, None, ys, stable, history,
-               device, return_status, chunk_filters, out)
+               device, return_status, chunk_filters, out, recompute_predict_quadrature)
     res = (out['ms'], out['mean'], out['nell'])
     return res + (out['status'],) if return_status else res
 
 
 def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, measurement_cond_pdf, scms0, mean0,
                        scale0, ys, stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
-                       return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None):
+                       return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None,
+                      recompute_predict_quadrature: bool = False):
     """Scaled-central-moment filter, mirror of ``mfs/one_dim/filtering.py:164-240``.
     Returns ``(scmss, means, scales, nell)``."""
     fn = _check_transition(state_cond_scaled_central_moments, 'scaled', 'state_cond_scaled_central_moments')
@@ -268,6 +278,6 @@ def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, m
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_scaled_central_moments and state_cond_mean_var must come from the same factory')
     out = _run('scaled', fn.spec, _check_measurement(measurement_cond_pdf), scms0, mean0, scale0, ys, stable,
-               history, device, return_status, chunk_filters, out)
+               history, device, return_status, chunk_filters, out, recompute_predict_quadrature)
     res = (out['ms'], out['mean'], out['scale'], out['nell'])
     return res + (out['status'],) if return_status else res

@@ -57,7 +57,7 @@ def filter_1d(mode, transition, measurement, ms0, ys, mean0=None, scale0=None, s
               num_threads=0):
     """Run the C oracle.  ``transition`` is any member of a ``mfs_b200`` factory tuple (only its spec is used),
     ``measurement`` a ``MeasurementFunctor``.  Returns a dict like ``mfs_b200.one_dim.filtering._run``."""
-    from mfs_b200 import _lib as P
+    from mfs_b200 import _lib as P  # struct mirror only
     from mfs_b200.functors import pack_params
     spec = transition.spec
     ys = np.asarray(ys)

@@ -13,6 +13,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 128 * 4
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 mode = sys.argv[4] if len(sys.argv) > 4 else 'raw'
+recompute = os.environ.get('MFS_RECOMPUTE', '0') == '1'
 history = sys.argv[5] if len(sys.argv) > 5 else 'full'
 dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
 fam = sde_cond_moments_tme(drift, disp, dt, 3)
@@ -21,9 +22,9 @@ for _ in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if mode == 'raw':
-        out = moment_filter_rms(fam[0], pmf, ic.rms, ys, history=history, return_status=True)
+        out = moment_filter_rms(fam[0], pmf, ic.rms, ys, history=history, return_status=True, recompute_predict_quadrature=recompute)
     else:
-        out = moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys, history=history, return_status=True)
+        out = moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys, history=history, return_status=True, recompute_predict_quadrature=recompute)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
