@@ -36,9 +36,14 @@ METRIC = 'benes_bernoulli_filter_steps_per_s'
 UNIT = 'filter-steps/s'
 
 
-def work_per_step(N: int) -> float:
-    """Algorithmic FP64 flop per filter-step, SURVEY.md 8(d): W(N) = 2/3 N^3 + 85 N^2 + 130 N + 30."""
-    return 2. / 3. * N ** 3 + 85. * N ** 2 + 130. * N + 30.
+def work_per_step(N: int, two_quadratures: bool) -> float:
+    """Algorithmic FP64 flop per filter-step.  SURVEY.md 8(d): W(N) = 2 W_quad + W_pred + W_upd
+    = 2/3 N^3 + 85 N^2 + 130 N + 30 for the literal recursion (two moment quadratures per step), with
+    W_quad = N^3/3 + N^2/2 + 4N [moments -> Jacobi coefficients] + 20 N (N+1) [tridiagonal QL].  The default kernel
+    re-uses the posterior atoms as the prediction quadrature, i.e. it runs ONE QL per step (the second quadrature
+    keeps only its Jacobi/pivot part): W_reuse(N) = W(N) - 20 N (N+1).  Only flops actually required are claimed."""
+    w = 2. / 3. * N ** 3 + 85. * N ** 2 + 130. * N + 30.
+    return w if two_quadratures else w - 20. * N * (N + 1)
 
 
 def measured_peaks():
@@ -223,11 +228,26 @@ def main():
         if args.mode == 'central':
             out_bufs['mean'] = torch.empty((B,), dtype=torch.float64, device=dev)
 
-    def step(ys_in, bufs, history):
+    def step(ys_in, bufs, history, literal=False):
         if args.mode == 'raw':
-            return moment_filter_rms(fam[0], pmf, ic.rms, ys_in, history=history, return_status=True, out=bufs)
+            return moment_filter_rms(fam[0], pmf, ic.rms, ys_in, history=history, return_status=True, out=bufs,
+                                     recompute_predict_quadrature=literal)
         return moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys_in, history=history, return_status=True,
-                                 out=bufs)
+                                 out=bufs, recompute_predict_quadrature=literal)
+
+    def timed(fn, n):
+        """n calls of fn bracketed by barriers; returns max-over-ranks milliseconds (CUDA events)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
     fp64_peak, _ = mfs_b200.fp64_peak(local_rank, 4096)      # roofline denominator, measured on this GPU
     for _ in range(args.warmup):
@@ -263,6 +283,28 @@ def main():
     diverged, live, launches_all = float(agg[0]) / world, float(agg[1]) / world, int(agg[2])
     steps_per_launch = B * T
     value = world * args.steps * steps_per_launch / (total_ms * 1e-3)
+
+    # secondary figures (same buffers, same data): the literal two-quadrature recursion, and the reference's own
+    # horizon T=100 (mfs/one_dim/ss_models.py:29), where ~1 % of the raw-moment filters diverge instead of ~43 %
+    step(ys, out_bufs, args.history, literal=True)
+    ms_lit = timed(lambda: step(ys, out_bufs, args.history, literal=True), args.steps)
+    value_literal = world * args.steps * steps_per_launch / (ms_lit * 1e-3)
+    kernel_ms_lit = ms_lit / args.steps
+    T100 = min(100, T)
+    ys100 = ys[:, :T100].contiguous()
+    bufs100 = {'nell': out_bufs['nell'], 'status': out_bufs['status']}
+    if args.history == 'full':
+        bufs100['ms'] = out_bufs['ms'].view(-1)[:B * T100 * M]
+        if args.mode == 'central':
+            bufs100['mean'] = out_bufs['mean'].view(-1)[:B * T100]
+    elif args.history == 'last':
+        bufs100['ms'] = out_bufs['ms']
+        if args.mode == 'central':
+            bufs100['mean'] = out_bufs['mean']
+    res100 = step(ys100, bufs100, args.history)
+    ms100 = timed(lambda: step(ys100, bufs100, args.history), args.steps)
+    value_t100 = world * args.steps * B * T100 / (ms100 * 1e-3)
+    div100 = float((res100[-1] >= 0).double().mean().item())
 
     # ---- e2e: host buffers through the public API (H2D + kernel + D2H every step) ----
     e2e = None
@@ -322,7 +364,8 @@ def main():
 
     if rank == 0:
         peaks, peaks_src = measured_peaks()
-        W = work_per_step(N)
+        W = work_per_step(N, two_quadratures=False)
+        W_lit = work_per_step(N, two_quadratures=True)
         achieved_tf = W * steps_per_launch / (kernel_ms_avg * 1e-3) / 1e12
         alg_bytes = (1 + (8 * M if args.history == 'full' else 0)) * steps_per_launch
         traffic = None
@@ -353,6 +396,11 @@ def main():
                                  'algorithmic_bytes_per_launch': alg_bytes}},
             'clocks': clocks, 'gpu_launches': launches_all, 'e2e': e2e, 'e2e_nell_only': e2e_nell,
             'diverged_frac': diverged, 'live_step_frac': live, 'wall_s_timed_region': t_wall,
+            'literal_two_quadratures': {
+                'value': value_literal, 'unit': UNIT, 'kernel_ms': kernel_ms_lit, 'flop_per_filter_step': W_lit,
+                'roofline_frac': W_lit * steps_per_launch / (kernel_ms_lit * 1e-3) / fp64_peak,
+                'note': 'MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE: second moment_quadrature per step, as filtering.py:78'},
+            'reference_horizon_T100': {'value': value_t100, 'unit': UNIT, 'T': T100, 'diverged_frac': div100},
         }
         if world == 1 and not args.no_cpu:
             v, cores, sample, _ = cpu_baseline(N, T)

@@ -14,7 +14,7 @@
  *   - plain C, no torch / CUDA types in signatures: device pointers are `void*`/`double*`, the stream is `void*`
  *     (a cudaStream_t; NULL = legacy default stream).
  *   - the caller owns every buffer; `mfs_filter_1d` never allocates.  `mfs_filter_1d_host` (host buffers) owns a
- *     per-call device workspace that it allocates and frees itself.
+ *     device staging workspace, cached between calls and returned by mfs_release_cached_memory().
  *   - return value 0 = launched/completed; negative = argument / CUDA error, text via mfs_last_error()
  *     (thread-local).  NUMERICAL failure is not an error: like the JAX scan it yields NaN from the failing step
  *     onwards, and status_out[b] = index of the first failed step (-1: none).
@@ -139,6 +139,10 @@ int mfs_filter_1d(const mfs_filter1d_args* a, void* stream);
  * pipelined H2D -> kernel -> D2H on `device` (double-buffered, two streams); returns after the last D2H completed.
  * `chunk_filters` = 0 picks a default. */
 int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_filters);
+
+/* mfs_filter_1d_host keeps its device staging buffers cached between calls (same shapes -> no cudaMalloc/cudaFree in
+ * steady state).  This returns every idle cached buffer to the driver. */
+int mfs_release_cached_memory(void);
 
 /* Batched moment quadrature (mfs/one_dim/quadtures.py:83-133): ms[B][2N] -> weights[B][N], nodes[B][N] (ascending
  * nodes when sort_nodes != 0).  mean/scale may be NULL (0 / 1).  Device pointers. */

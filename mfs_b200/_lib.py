@@ -47,7 +47,7 @@ class Filter1dArgs(ctypes.Structure):
 
 
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
-           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak')
+           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory')
 
 _lib = None
 _lock = threading.Lock()
@@ -106,6 +106,11 @@ def lib() -> ctypes.CDLL:
 def check(rc: int):
     if rc != 0:
         raise MfsError(lib().mfs_last_error().decode() or f'libmfs_b200 returned {rc}')
+
+
+def release_cached_memory():
+    """Return the cached device staging buffers of the host-buffer path to the driver."""
+    check(lib().mfs_release_cached_memory())
 
 
 def launch_count() -> int:

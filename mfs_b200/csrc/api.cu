@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,39 @@ static int fail(const char* fmt, ...) {
     cudaError_t e__ = (call);                                                                \
     if (e__ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e__));    \
   } while (0)
+
+// Device workspace of the host-buffer entry point.  Blocks are cached per (device, size) between calls so that a
+// pipeline calling mfs_filter_1d_host repeatedly with the same shapes pays cudaMalloc/cudaFree (which synchronise the
+// device) once; mfs_release_cached_memory() gives everything back.
+struct WsBlock { int device; size_t bytes; void* ptr; bool busy; };
+static std::mutex g_ws_mutex;
+static std::vector<WsBlock> g_ws;
+
+static cudaError_t ws_alloc(int device, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (WsBlock& b : g_ws)
+    if (!b.busy && b.device == device && b.bytes == bytes) { b.busy = true; *out = b.ptr; return cudaSuccess; }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // give cached idle blocks back and retry once
+    for (size_t i = 0; i < g_ws.size();) {
+      if (!g_ws[i].busy && g_ws[i].device == device) { cudaFree(g_ws[i].ptr); g_ws.erase(g_ws.begin() + i); } else ++i;
+    }
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+  }
+  g_ws.push_back({device, bytes, p, true});
+  *out = p;
+  return cudaSuccess;
+}
+
+static void ws_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (WsBlock& b : g_ws)
+    if (b.ptr == p) { b.busy = false; return; }
+}
 
 static int ys_elem_size(int dtype) { return dtype == MFS_YS_U8 ? 1 : dtype == MFS_YS_I32 ? 4 : 8; }
 
@@ -201,10 +235,11 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
 
   const int esz = ys_elem_size(a->ys_dtype);
   if (chunk_filters <= 0) {
-    // aim for ~256 MiB of output per chunk, at least 8 waves of CTAs on 148 SMs
+    // ~1 GiB of traffic per chunk, but never fewer than two CTAs per SM (the D2H copy, not the kernel, is the
+    // bottleneck of the full-history mode: small chunks shorten the un-overlapped head and tail of the pipeline)
     const int64_t per_filter = (a->out_mode == MFS_OUT_FULL ? T * (M + 2) * 8 : (M + 4) * 8) + T * esz;
-    chunk_filters = (256LL << 20) / (per_filter > 0 ? per_filter : 1);
-    if (chunk_filters < 148LL * 4 * kBlock) chunk_filters = 148LL * 4 * kBlock;
+    chunk_filters = (1LL << 30) / (per_filter > 0 ? per_filter : 1);
+    if (chunk_filters < 148LL * 2 * kBlock) chunk_filters = 148LL * 2 * kBlock;
   }
   chunk_filters = (chunk_filters + kBlock - 1) / kBlock * kBlock;
   if (chunk_filters > a->B) chunk_filters = a->B;
@@ -227,8 +262,8 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
   auto cleanup = [&]() {
     for (Slot& k : slot) {
       if (k.s) cudaStreamSynchronize(k.s);
-      cudaFree(k.ys); cudaFree(k.ms0); cudaFree(k.mean0); cudaFree(k.scale0); cudaFree(k.tprm); cudaFree(k.mprm);
-      cudaFree(k.ms_out); cudaFree(k.mean_out); cudaFree(k.scale_out); cudaFree(k.nell); cudaFree(k.status);
+      ws_free(k.ys); ws_free(k.ms0); ws_free(k.mean0); ws_free(k.scale0); ws_free(k.tprm); ws_free(k.mprm);
+      ws_free(k.ms_out); ws_free(k.mean_out); ws_free(k.scale_out); ws_free(k.nell); ws_free(k.status);
       if (k.s) cudaStreamDestroy(k.s);
     }
   };
@@ -242,17 +277,17 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
   for (int k = 0; k < nslots; ++k) {
     Slot& s = slot[k];
     MFS_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
-    if (T > 0) MFS_TRY(cudaMalloc(&s.ys, (size_t)(C * T * esz)));
-    MFS_TRY(cudaMalloc(&s.ms0, sizeof(double) * (per_ms0 ? C * M : M)));
-    if (a->mean0) MFS_TRY(cudaMalloc(&s.mean0, sizeof(double) * (per_mean0 ? C : 1)));
-    if (a->scale0) MFS_TRY(cudaMalloc(&s.scale0, sizeof(double) * (per_scale0 ? C : 1)));
-    MFS_TRY(cudaMalloc(&s.tprm, sizeof(double) * MFS_MAX_PARAMS * (per_t ? C : 1)));
-    MFS_TRY(cudaMalloc(&s.mprm, sizeof(double) * MFS_MAX_PARAMS * (per_m ? C : 1)));
-    if (out_ms) MFS_TRY(cudaMalloc(&s.ms_out, sizeof(double) * out_ms));
-    if (out_aux && a->mean_out) MFS_TRY(cudaMalloc(&s.mean_out, sizeof(double) * out_aux));
-    if (out_aux && a->scale_out) MFS_TRY(cudaMalloc(&s.scale_out, sizeof(double) * out_aux));
-    MFS_TRY(cudaMalloc(&s.nell, sizeof(double) * C));
-    if (a->status_out) MFS_TRY(cudaMalloc(&s.status, sizeof(int32_t) * C));
+    if (T > 0) MFS_TRY(ws_alloc(device, (size_t)(C * T * esz), reinterpret_cast<void**>(&s.ys)));
+    MFS_TRY(ws_alloc(device, sizeof(double) * (per_ms0 ? C * M : M), reinterpret_cast<void**>(&s.ms0)));
+    if (a->mean0) MFS_TRY(ws_alloc(device, sizeof(double) * (per_mean0 ? C : 1), reinterpret_cast<void**>(&s.mean0)));
+    if (a->scale0) MFS_TRY(ws_alloc(device, sizeof(double) * (per_scale0 ? C : 1), reinterpret_cast<void**>(&s.scale0)));
+    MFS_TRY(ws_alloc(device, sizeof(double) * MFS_MAX_PARAMS * (per_t ? C : 1), reinterpret_cast<void**>(&s.tprm)));
+    MFS_TRY(ws_alloc(device, sizeof(double) * MFS_MAX_PARAMS * (per_m ? C : 1), reinterpret_cast<void**>(&s.mprm)));
+    if (out_ms) MFS_TRY(ws_alloc(device, sizeof(double) * out_ms, reinterpret_cast<void**>(&s.ms_out)));
+    if (out_aux && a->mean_out) MFS_TRY(ws_alloc(device, sizeof(double) * out_aux, reinterpret_cast<void**>(&s.mean_out)));
+    if (out_aux && a->scale_out) MFS_TRY(ws_alloc(device, sizeof(double) * out_aux, reinterpret_cast<void**>(&s.scale_out)));
+    MFS_TRY(ws_alloc(device, sizeof(double) * C, reinterpret_cast<void**>(&s.nell)));
+    if (a->status_out) MFS_TRY(ws_alloc(device, sizeof(int32_t) * C, reinterpret_cast<void**>(&s.status)));
   }
 
   int k = 0;
@@ -321,6 +356,14 @@ int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const doubl
   }
   if (e != cudaSuccess) return fail("quadrature launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (size_t i = 0; i < g_ws.size();) {
+    if (!g_ws[i].busy) { cudaFree(g_ws[i].ptr); g_ws.erase(g_ws.begin() + i); } else ++i;
+  }
   return 0;
 }
 
