@@ -5,7 +5,10 @@
 
 namespace mfs {
 
-constexpr int kBlock = 128;
+#ifndef MFS_BLOCK
+#define MFS_BLOCK 128   // threads per CTA (64 / 96 / 256 measured no faster, profiles/r1_occupancy_sweep.md)
+#endif
+constexpr int kBlock = MFS_BLOCK;
 
 // CTAs of 128 threads per SM that the register allocation must allow.  The step is a long dependent FP64 chain (QL
 // rotations), so resident warps are what hides the DFMA latency; measured on B200 (profiles/r1_occupancy_sweep.md):
