@@ -158,6 +158,9 @@ def triangular_solve(a, b, left_side=False, lower=False, transpose_a=False, conj
 
 def eigh(x, lower=True, symmetrize_input=True, sort_eigenvalues=True):
     x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 3:      # batched, like jax.lax.linalg.eigh
+        pairs = [eigh(m, lower, symmetrize_input, sort_eigenvalues) for m in x]
+        return _wrap(np.stack([p[0] for p in pairs])), _wrap(np.stack([p[1] for p in pairs]))
     if symmetrize_input:
         x = 0.5 * (x + x.T)
     if not np.all(np.isfinite(x)):

@@ -16,7 +16,7 @@ reference's code, unmodified, from where it lies:
   mfs/utils.py               GaussianSum1D.new, ldl, ldl_chol
   mfs/multi_dims/multi_indices.py   (pure NumPy)          -> golden_multi_indices.npz
   mfs/multi_dims/moments.py  Kan--Magnus NumPy branches   -> golden_kan_moments.npz
-  mfs/multi_dims/quadratures.py, filtering.py             -> golden_nd_*.npz
+  mfs/multi_dims/quadratures.py, filtering.py, ss_models.py (prey_predator), utils.GaussianSumND -> golden_nd.npz
 
 The third-party ``tme`` package is absent, so fixtures whose transition moments are TME expansions take those
 callables from ``oracle/mfs_oracle.py`` (definition-driven restatement) and are labelled ``*_tme*``: they pin the
@@ -199,8 +199,90 @@ def golden_filter_1d():
     print('golden_filter_1d_well.npz')
 
 
+def synth_prey_predator(rng, T, dt, substeps=100):
+    """Milstein simulation of the Lotka--Volterra SDE + Bernoulli observations (mfs/multi_dims/ss_models.py:69-93),
+    NumPy RNG."""
+    alp, beta, delta, gamma, sigma = 4., 4., 4., 4., 0.1
+    x = np.array([1., 1.]) + np.sqrt(0.0015) * rng.standard_normal(2)
+    ddt = dt / substeps
+    xs = np.empty((T, 2))
+    for t in range(T):
+        for _ in range(substeps):
+            ddw = np.sqrt(ddt) * rng.standard_normal(2)
+            drift = x * (x[::-1] * np.array([-beta, delta]) + np.array([alp, -gamma]))
+            x = x + drift * ddt + sigma * x * ddw + 0.5 * sigma ** 2 * x * (ddw ** 2 - ddt)
+        xs[t] = x
+    ys = (rng.random(T) < 1 / (1 + np.exp(-xs[:, 0] ** 3 + 1))).astype(np.uint8)
+    return xs, ys
+
+
+def golden_multi_indices():
+    from mfs.multi_dims.multi_indices import (generate_graded_lexico_multi_indices,
+                                              gram_and_hankel_indices_graded_lexico)
+    out = {}
+    for d in (1, 2, 3, 5):
+        for up in (4, 6):
+            for lo in (0, 3):
+                out[f'gen/{d}_{up}_{lo}'] = generate_graded_lexico_multi_indices(d, up, lo)
+    for N, d in ((2, 2), (3, 2), (5, 2), (8, 2), (3, 3), (4, 1), (2, 4)):
+        out[f'gh/{N}_{d}'] = gram_and_hankel_indices_graded_lexico(N, d)
+    np.savez_compressed(os.path.join(HERE, 'golden_multi_indices.npz'), **out)
+    print('golden_multi_indices.npz')
+
+
+def golden_nd():
+    from mfs.multi_dims.multi_indices import (generate_graded_lexico_multi_indices,
+                                              gram_and_hankel_indices_graded_lexico)
+    from mfs.multi_dims.quadratures import moment_quadrature_nd
+    from mfs.multi_dims.moments import raw_moments_mvn_kan, sde_cond_moments_euler_maruyama
+    from mfs.multi_dims.filtering import moment_filter_nd_rms, moment_filter_nd_cms
+    from mfs.multi_dims.ss_models import prey_predator
+    d = 2
+    out = {}
+    # Kan--Magnus moments + nd quadrature of a correlated Gaussian (tests/test_multi_dim_quadrature.py setting)
+    mean = np.array([0.3, -0.2])
+    cov = np.array([[1.1, 0.3], [0.3, 0.7]])
+    for N in (3, 4, 5):
+        mis = generate_graded_lexico_multi_indices(d, 2 * N - 1, 0)
+        inds = gram_and_hankel_indices_graded_lexico(N, d)
+        rms = np.array([raw_moments_mvn_kan(mean, cov, n) for n in mis])
+        cms = np.array([raw_moments_mvn_kan(mean - mean, cov, n) for n in mis])
+        w, x = moment_quadrature_nd(jnp.asarray(rms), inds)
+        wc, xc = moment_quadrature_nd(jnp.asarray(cms), inds, jnp.asarray(mean))
+        out[f'quad/N{N}/rms'], out[f'quad/N{N}/cms'] = rms, cms
+        out[f'quad/N{N}/w'], out[f'quad/N{N}/x'] = np.asarray(w), np.asarray(x)
+        out[f'quad/N{N}/wc'], out[f'quad/N{N}/xc'] = np.asarray(wc), np.asarray(xc)
+    out['quad/mean'], out['quad/cov'] = mean, cov
+    # prey--predator filters, Euler--Maruyama + Normal transition (100 % reference code, Kan--Magnus NumPy branch)
+    rng = np.random.Generator(np.random.PCG64(671))
+    for N, T in ((3, 12), (4, 6)):
+        mis = generate_graded_lexico_multi_indices(d, 2 * N - 1, 0)
+        inds = gram_and_hankel_indices_graded_lexico(N, d)
+        dt, _, ts, gs, drift, dispersion, emission, pmf, _ = prey_predator(mis)
+        xs, ys = synth_prey_predator(rng, T, dt)
+        f_rms, f_cms, _, f_mean, _ = sde_cond_moments_euler_maruyama(drift, dispersion, dt, mis)
+        rmss, nell = moment_filter_nd_rms((f_rms, 'index'), pmf, jnp.asarray(ys), (jnp.asarray(mis), inds), gs.rms)
+        cmss, means, nell_c = moment_filter_nd_cms((f_cms, 'index'), f_mean, pmf, jnp.asarray(ys),
+                                                   (jnp.asarray(mis), inds), gs.cms, gs.mean)
+        out[f'pp/N{N}/ys'], out[f'pp/N{N}/rms0'], out[f'pp/N{N}/cms0'] = ys, np.asarray(gs.rms), np.asarray(gs.cms)
+        out[f'pp/N{N}/mean0'] = np.asarray(gs.mean)
+        out[f'pp/N{N}/rmss'], out[f'pp/N{N}/nell'] = np.asarray(rmss), float(nell)
+        out[f'pp/N{N}/cmss'], out[f'pp/N{N}/means'], out[f'pp/N{N}/nell_c'] = np.asarray(cmss), np.asarray(means), \
+            float(nell_c)
+    # initial moments of the paper setting N = 5
+    mis = generate_graded_lexico_multi_indices(d, 9, 0)
+    dt, _, ts, gs, *_ = prey_predator(mis)
+    out['pp/N5/rms0'], out['pp/N5/cms0'], out['pp/N5/mean0'] = np.asarray(gs.rms), np.asarray(gs.cms), np.asarray(gs.mean)
+    np.savez_compressed(os.path.join(HERE, 'golden_nd.npz'), **out)
+    print('golden_nd.npz')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d']
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd']
+    if 'multi_indices' in which:
+        golden_multi_indices()
+    if 'nd' in which:
+        golden_nd()
     if 'quadrature' in which:
         golden_quadrature_1d()
     if 'conversions' in which:
