@@ -121,6 +121,41 @@ typedef struct mfs_filter1d_args {
   int32_t reserved0;
 } mfs_filter1d_args;
 
+/* ---- d = 2 moment filter (mfs/multi_dims/filtering.py:210-344, quadratures.py:120-178) ------------------------------
+ * Moments are ordered graded-lexicographically (mfs/multi_dims/multi_indices.py): position of the multi-index (a, b)
+ * is (a+b)(a+b+1)/2 + a, z = N(2N+1) moments with |n| <= 2N-1; `inds` is the (3, s, s) int32 gather table of
+ * gram_and_hankel_indices_graded_lexico(N, 2), s = N(N+1)/2.  Transition: the Normal families of
+ * mfs/multi_dims/moments.py:257-411 for the Lotka--Volterra SDE of mfs/multi_dims/ss_models.py:40-61
+ * (trans_params = {alpha, beta, delta, gamma, sigma}); measurement: MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC on x[obs_dim]
+ * (prey--predator: {c0, c1} = {1, 1}, ss_models.py:63-67).  Device pointers. */
+typedef struct mfs_filternd_args {
+  int32_t abi_version;
+  int32_t mode;          /* MFS_MODE_RAW | MFS_MODE_CENTRAL */
+  int32_t N;             /* 2..6 */
+  int32_t d;             /* must be 2 */
+  int64_t B, T;
+  int32_t trans_id;      /* MFS_TRANS_EULER | MFS_TRANS_TME_NORMAL */
+  int32_t tme_order;     /* 1..2 */
+  int32_t meas_id;
+  int32_t obs_dim;
+  double dt;
+  const double* trans_params; int64_t trans_param_stride;   /* [B|1][8] */
+  const double* meas_params;  int64_t meas_param_stride;    /* [B|1][4] */
+  const double* ms0;   int64_t ms0_stride;                  /* [B|1][z] */
+  const double* mean0; int64_t mean0_stride;                /* [B|1][2], CENTRAL */
+  const uint8_t* ys;                                        /* [B][T] */
+  const int32_t* inds;                                      /* [3][s][s] */
+  int32_t out_mode;      /* MFS_OUT_* */
+  int32_t reserved0;
+  double* ms_out;        /* FULL [B][T][z] | LAST [B][z] */
+  double* mean_out;      /* FULL [B][T][2] | LAST [B][2] */
+  double* nell_out;      /* [B] */
+  int32_t* status_out;   /* [B] or NULL */
+} mfs_filternd_args;
+
+/* Enqueue B two-dimensional filters x T steps on `stream` (one warp per filter). */
+int mfs_filter_nd(const mfs_filternd_args* a, void* stream);
+
 /* ABI version of the loaded library. */
 int mfs_abi_version(void);
 

@@ -46,8 +46,26 @@ class Filter1dArgs(ctypes.Structure):
     ]
 
 
+class FilterNdArgs(ctypes.Structure):
+    """Mirror of ``mfs_filternd_args``."""
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('mode', ctypes.c_int32), ('N', ctypes.c_int32), ('d', ctypes.c_int32),
+        ('B', ctypes.c_int64), ('T', ctypes.c_int64),
+        ('trans_id', ctypes.c_int32), ('tme_order', ctypes.c_int32), ('meas_id', ctypes.c_int32),
+        ('obs_dim', ctypes.c_int32), ('dt', ctypes.c_double),
+        ('trans_params', ctypes.c_void_p), ('trans_param_stride', ctypes.c_int64),
+        ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
+        ('ms0', ctypes.c_void_p), ('ms0_stride', ctypes.c_int64),
+        ('mean0', ctypes.c_void_p), ('mean0_stride', ctypes.c_int64),
+        ('ys', ctypes.c_void_p), ('inds', ctypes.c_void_p),
+        ('out_mode', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('ms_out', ctypes.c_void_p), ('mean_out', ctypes.c_void_p), ('nell_out', ctypes.c_void_p),
+        ('status_out', ctypes.c_void_p),
+    ]
+
+
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
-           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory')
+           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd')
 
 _lib = None
 _lock = threading.Lock()
@@ -93,6 +111,8 @@ def lib() -> ctypes.CDLL:
                                                ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p]
         L.mfs_moment_quadrature_1d.restype = ctypes.c_int
+        L.mfs_filter_nd.argtypes = [ctypes.POINTER(FilterNdArgs), ctypes.c_void_p]
+        L.mfs_filter_nd.restype = ctypes.c_int
         L.mfs_launch_count.restype = ctypes.c_int64
         L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "filter1d.cuh"
+#include "filter_nd.cuh"
 
 namespace mfs {
 
@@ -355,6 +356,45 @@ int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const doubl
 #undef MFS_CASE
   }
   if (e != cudaSuccess) return fail("quadrature launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
+  if (!a) return fail("args is NULL");
+  if (a->abi_version != MFS_ABI_VERSION) return fail("abi_version %d != %d", a->abi_version, MFS_ABI_VERSION);
+  if (a->d != 2) return fail("only d = 2 is implemented (got d = %d)", a->d);
+  if (a->N < 2 || a->N > 6) return fail("N=%d outside [2, 6] for the 2-D filter", a->N);
+  if (a->mode != MFS_MODE_RAW && a->mode != MFS_MODE_CENTRAL) return fail("2-D filter: mode must be raw or central");
+  if (a->trans_id != MFS_TRANS_EULER && a->trans_id != MFS_TRANS_TME_NORMAL)
+    return fail("2-D filter: transition must be euler or tme_normal (Lotka--Volterra)");
+  if (a->trans_id == MFS_TRANS_TME_NORMAL && (a->tme_order < 1 || a->tme_order > 2)) return fail("2-D filter: tme_order must be 1 or 2");
+  if (a->meas_id != MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) return fail("2-D filter: measurement must be bernoulli_logistic_cubic");
+  if (a->obs_dim < 0 || a->obs_dim > 1) return fail("obs_dim must be 0 or 1");
+  if (a->B < 0 || a->T < 0) return fail("negative B or T");
+  if (a->B == 0) return 0;
+  if (!a->trans_params || !a->meas_params || !a->ms0 || !a->inds || !a->nell_out || (a->T > 0 && !a->ys))
+    return fail("NULL pointer argument");
+  if (a->mode == MFS_MODE_CENTRAL && (!a->mean0 || (a->out_mode != MFS_OUT_NONE && !a->mean_out))) return fail("mean0 / mean_out is NULL in central mode");
+  if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
+  NdArgs k;
+  k.mode = a->mode; k.trans_id = a->trans_id; k.tme_order = a->tme_order; k.meas_id = a->meas_id; k.obs_dim = a->obs_dim;
+  k.out_mode = a->out_mode; k.B = a->B; k.T = a->T; k.dt = a->dt;
+  k.trans_params = a->trans_params; k.trans_param_stride = a->trans_param_stride;
+  k.meas_params = a->meas_params; k.meas_param_stride = a->meas_param_stride;
+  k.ms0 = a->ms0; k.ms0_stride = a->ms0_stride; k.mean0 = a->mean0; k.mean0_stride = a->mean0_stride;
+  k.ys = a->ys; k.inds = a->inds; k.pos = nullptr;
+  k.ms_out = a->ms_out; k.mean_out = a->mean_out; k.nell_out = a->nell_out; k.status_out = a->status_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (a->N) {
+    case 2: e = launch_filter_nd<2>(k, s); break;
+    case 3: e = launch_filter_nd<3>(k, s); break;
+    case 4: e = launch_filter_nd<4>(k, s); break;
+    case 5: e = launch_filter_nd<5>(k, s); break;
+    case 6: e = launch_filter_nd<6>(k, s); break;
+  }
+  if (e != cudaSuccess) return fail("2-D filter launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -1,0 +1,447 @@
+// The batched 2-dimensional moment filter (prey--predator / Lotka--Volterra), one filter per WARP, matrices in shared
+// memory.  Restates mfs/multi_dims/filtering.py:258-277 (central) / :325-341 (raw) and
+// mfs/multi_dims/quadratures.py:149-178.
+//
+// Per half-step (quadrature):
+//   G = ms[inds[0]] (s x s, s = C(N+1, 2)); R = chol(G) in place (lane-parallel right-looking);
+//   for k = 0, 1:  K_k = R^-1 ms[inds[1+k]] R^-T  (forward substitutions, one lane per column / row), symmetrised;
+//   both K_k are diagonalised TOGETHER by a cyclic Jacobi eigenvalue iteration with round-robin ordering (the K_k are
+//   dense, not tridiagonal, in d >= 2): the up-to-(s/2) disjoint rotations of a round for both matrices are computed
+//   by different lanes and applied to rows, then columns, then eigenvector columns in parallel;
+//   nodes (lam1_i, lam2_j) + mean, weights <v1_i, v2_j> v1_i[0] v2_j[0]  (s^2 signed weights).
+// Prediction uses the Normal transition families (Euler--Maruyama, TME + Normal of order 1/2) of the Lotka--Volterra
+// SDE; the product moments of N(mu - m, C) come from the recursion E[x^{n+e_i}] = mu_i E[x^n] + sum_j C_ij n_j
+// E[x^{n-e_j}], which equals the Kan--Magnus sum of mfs/multi_dims/moments.py:111-154 (checked in the tests).
+// Eigenvector signs/order are arbitrary; every consumer is a sum over all s^2 nodes, so they cancel.
+#pragma once
+#include "models.cuh"
+
+namespace mfs {
+
+constexpr int kNdWarps = 4;  // warps (filters) per CTA
+
+struct NdArgs {
+  int32_t mode;        // MFS_MODE_RAW / MFS_MODE_CENTRAL
+  int32_t trans_id;    // MFS_TRANS_EULER / MFS_TRANS_TME_NORMAL
+  int32_t tme_order;   // 1 or 2
+  int32_t meas_id;     // MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC on x[obs_dim]
+  int32_t obs_dim;
+  int32_t out_mode;
+  int64_t B, T;
+  double dt;
+  const double* trans_params;  // {alpha, beta, delta, gamma, sigma}
+  int64_t trans_param_stride;
+  const double* meas_params;
+  int64_t meas_param_stride;
+  const double* ms0;           // [B|1][z]
+  int64_t ms0_stride;
+  const double* mean0;         // [B|1][2]
+  int64_t mean0_stride;
+  const unsigned char* ys;     // [B][T] uint8
+  const int32_t* inds;         // [3][s][s] gather tables (gram_and_hankel_indices_graded_lexico)
+  const int32_t* pos;          // [2N][2N] position of multi-index (a, b) in the moment vector, -1 if |n| > 2N-1
+  double* ms_out;              // FULL [B][T][z]; LAST [B][z]
+  double* mean_out;            // FULL [B][T][2]; LAST [B][2]
+  double* nell_out;
+  int32_t* status_out;
+};
+
+MFS_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Lotka--Volterra drift x1 (alpha - beta x2), x2 (delta x1 - gamma), dispersion diag(sigma x): conditional mean and
+// covariance.  Euler: mfs/multi_dims/moments.py:291-293.  TME order 2: tme.mean_and_cov restated (closed forms
+// verified in the tests against a symbolic application of the generator, and SURVEY.md Appendix B).
+MFS_DEV void lv_mean_cov(int trans_id, int order, double x1, double x2, double dt, const double* p, double& m1,
+                         double& m2, double& c11, double& c12, double& c22) {
+  const double al = p[0], be = p[1], de = p[2], ga = p[3], sg2 = p[4] * p[4];
+  const double a1 = x1 * (al - be * x2), a2 = x2 * (de * x1 - ga);
+  m1 = fma(dt, a1, x1);
+  m2 = fma(dt, a2, x2);
+  c11 = sg2 * x1 * x1 * dt;
+  c22 = sg2 * x2 * x2 * dt;
+  c12 = 0.0;
+  if (trans_id == MFS_TRANS_TME_NORMAL && order >= 2) {
+    const double h = 0.5 * dt * dt;
+    // A^2 x_i = a . grad(a_i) + 1/2 tr(bb^T Hess a_i);  Hess a_1 = [[0,-beta],[-beta,0]], bb^T diagonal -> trace term 0
+    m1 = fma(h, a1 * (al - be * x2) - be * x1 * a2, m1);
+    m2 = fma(h, de * x2 * a1 + a2 * (de * x1 - ga), m2);
+    c11 = fma(dt * dt * sg2 * x1 * x1, 2.0 * al - 2.0 * be * x2 + 0.5 * sg2, c11);
+    c22 = fma(dt * dt * sg2 * x2 * x2, 2.0 * de * x1 - 2.0 * ga + 0.5 * sg2, c22);
+    c12 = 0.5 * dt * dt * sg2 * x1 * x2 * (de * x1 - be * x2);
+  }
+}
+
+template <int N>
+struct NdDims {
+  static constexpr int S = N * (N + 1) / 2;        // basis size
+  static constexpr int Z = N * (2 * N + 1);        // number of moments, |n| <= 2N-1
+  static constexpr int M = 2 * N;                  // orders 0..2N-1 per dimension
+  static constexpr int SS = S * S;
+  // per-warp shared memory in doubles: ms, R, K[2], V[2], wts, lam[2], rotation (c, s) for up to 32 pairs
+  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 64;
+  static constexpr int kInts = 64;                 // rotation (p, q)
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Quadrature: ms (shared) -> lam[2][S], V[2][S][S] (eigenvectors in columns), wts[S][S].  Returns false on failure.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+MFS_DEV int quadrature_nd(const NdArgs& P, double* sm, int* si, int lane) {   // 0 ok, 1 pivot, 2 no convergence, 3 NaN
+  using D = NdDims<N>;
+  constexpr int S = D::S, SS = D::SS;
+  double* ms = sm;
+  double* R = ms + D::Z;
+  double* K = R + SS;          // K[0], K[1]
+  double* V = K + 2 * SS;      // V[0], V[1]
+  double* wts = V + 2 * SS;
+  double* lam = wts + SS;      // lam[0][S], lam[1][S]
+  double* rot = lam + 2 * S;   // c[32], s[32]
+
+  // gather G and both Hankel matrices
+  for (int e = lane; e < SS; e += 32) {
+    R[e] = ms[__ldg(P.inds + e)];
+    K[e] = ms[__ldg(P.inds + SS + e)];
+    K[SS + e] = ms[__ldg(P.inds + 2 * SS + e)];
+  }
+  __syncwarp();
+
+  // Cholesky (lower, in place, right-looking).  Failure <=> a pivot is not > 0 (jax: NaN-filled factor).
+  bool ok = true;
+  for (int j = 0; j < S; ++j) {
+    const double piv = R[j * S + j];
+    if (!(piv > 0.0)) { ok = false; break; }
+    const double rinv = rsqrt_fast(piv);
+    __syncwarp();
+    for (int i = j + lane; i < S; i += 32) R[i * S + j] = (i == j) ? piv * rinv : R[i * S + j] * rinv;
+    __syncwarp();
+    // trailing update: R[i][k] -= R[i][j] R[k][j],  j < k <= i
+    const int m = S - j - 1;
+    for (int e = lane; e < m * m; e += 32) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) R[i * S + k] = fma(-R[i * S + j], R[k * S + j], R[i * S + k]);
+    }
+    __syncwarp();
+  }
+  if (!ok) return 1;
+
+  // K_k <- R^-1 H_k R^-T.  Step 1: columns of Y = R^-1 H (lane per (k, column)); step 2: rows of K = Y R^-T.
+  for (int task = lane; task < 2 * S; task += 32) {
+    double* A = K + (task / S) * SS;
+    const int c = task % S;
+    for (int i = 0; i < S; ++i) {
+      double acc = A[i * S + c];
+      for (int q = 0; q < i; ++q) acc = fma(-R[i * S + q], A[q * S + c], acc);
+      A[i * S + c] = acc / R[i * S + i];
+    }
+  }
+  __syncwarp();
+  for (int task = lane; task < 2 * S; task += 32) {
+    double* A = K + (task / S) * SS;
+    const int r = task % S;
+    for (int i = 0; i < S; ++i) {
+      double acc = A[r * S + i];
+      for (int q = 0; q < i; ++q) acc = fma(-R[i * S + q], A[r * S + q], acc);
+      A[r * S + i] = acc / R[i * S + i];
+    }
+  }
+  __syncwarp();
+  // symmetrise (jax.lax.linalg.eigh symmetrises its input) and set V = I
+  for (int e = lane; e < 2 * SS; e += 32) {
+    const int k = e / SS, r = (e % SS) / S, c = e % S;
+    if (c < r) {
+      const double v = 0.5 * (K[k * SS + r * S + c] + K[k * SS + c * S + r]);
+      K[k * SS + r * S + c] = v;
+      K[k * SS + c * S + r] = v;
+    }
+    V[e] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+
+  // cyclic Jacobi, round-robin ordering, both matrices at once
+  constexpr int Mp = (S % 2 == 0) ? S : S + 1;   // players (with a dummy when S is odd)
+  constexpr int HP = Mp / 2;                     // pairs per round and matrix
+  bool converged = false;
+  for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
+    for (int round = 0; round < Mp - 1; ++round) {
+      if (lane < 2 * HP) {
+        const int k = lane / HP, slot = lane % HP;
+        int p = (slot == 0) ? (Mp - 1) : (round + slot) % (Mp - 1);
+        int q = (round - slot + (Mp - 1)) % (Mp - 1);
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < S && p != q) {
+          const double* A = K + k * SS;
+          const double apq = A[p * S + q], app = A[p * S + p], aqq = A[q * S + q];
+          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) + 1e-20 * (fabs(app) + fabs(aqq))) {
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            c = rsqrt(fma(t, t, 1.0));
+            s = t * c;
+          }
+        } else {
+          p = q = -1;
+        }
+        rot[lane] = c;
+        rot[32 + lane] = s;
+        si[lane] = p;
+        si[32 + lane] = q;
+      }
+      __syncwarp();
+      // rows: (A[p][j], A[q][j]) <- (c A[p][j] - s A[q][j], s A[p][j] + c A[q][j])
+      for (int e = lane; e < 2 * HP * S; e += 32) {
+        const int pr = e / S, j = e % S, p = si[pr], q = si[32 + pr];
+        if (p >= 0) {
+          double* A = K + (pr / HP) * SS;
+          const double c = rot[pr], s = rot[32 + pr];
+          const double x = A[p * S + j], y = A[q * S + j];
+          A[p * S + j] = fma(c, x, -s * y);
+          A[q * S + j] = fma(s, x, c * y);
+        }
+      }
+      __syncwarp();
+      // columns of A and of V
+      for (int e = lane; e < 2 * HP * S; e += 32) {
+        const int pr = e / S, i = e % S, p = si[pr], q = si[32 + pr];
+        if (p >= 0) {
+          double* A = K + (pr / HP) * SS;
+          double* W = V + (pr / HP) * SS;
+          const double c = rot[pr], s = rot[32 + pr];
+          const double x = A[i * S + p], y = A[i * S + q];
+          A[i * S + p] = fma(c, x, -s * y);
+          A[i * S + q] = fma(s, x, c * y);
+          const double u = W[i * S + p], v = W[i * S + q];
+          W[i * S + p] = fma(c, u, -s * v);
+          W[i * S + q] = fma(s, u, c * v);
+        }
+      }
+      __syncwarp();
+    }
+    // convergence: off-diagonal mass against diagonal mass, both matrices
+    double off = 0.0, dia = 0.0;
+    for (int e = lane; e < 2 * SS; e += 32) {
+      const int r = (e % SS) / S, c = e % S;
+      const double v = K[e];
+      if (r == c) dia = fma(v, v, dia); else off = fma(v, v, off);
+    }
+    off = warp_sum(off);
+    dia = warp_sum(dia);
+    // rounding keeps the off-diagonal mass near (eps |K|)^2 * (#entries) ~ 1e-30 |K|^2: stop an order above that floor
+    converged = !(off > 1e-28 * dia);
+    if (!(off == off)) return 3;
+  }
+  if (!converged) return 2;
+  for (int e = lane; e < 2 * S; e += 32) lam[e] = K[(e / S) * SS + (e % S) * S + (e % S)];
+  __syncwarp();
+  // weights: <v1_i, v2_j> v1_i[0] v2_j[0]   (quadratures.py:169-170)
+  for (int e = lane; e < SS; e += 32) {
+    const int i = e / S, j = e % S;
+    double dot = 0.0;
+    for (int r = 0; r < S; ++r) dot = fma(V[r * S + i], V[SS + r * S + j], dot);
+    wts[e] = dot * V[i] * V[SS + j];
+  }
+  __syncwarp();
+  return 0;
+}
+
+// accumulate acc[pos(a, b)] += wgt * M[a][b] for the Gaussian product moments of N((mu1, mu2), C) -- registers only
+template <int N>
+MFS_DEV void accumulate_gaussian_moments(double wgt, double mu1, double mu2, double c11, double c12, double c22,
+                                         double (&acc)[NdDims<N>::Z]) {
+  constexpr int M = 2 * N;
+  // rows indexed by b (power of x2); within a row a = 0..M-1-b.  M[a+1][b] = mu1 M[a][b] + c11 a M[a-1][b] + c12 b M[a][b-1]
+  double prev[M], cur[M], prev2[M];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { prev[a] = 0.0; prev2[a] = 0.0; cur[a] = 0.0; }
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    // first entry of the row: M[0][b] = mu2 M[0][b-1] + c22 (b-1) M[0][b-2]
+    if (b == 0) cur[0] = 1.0;
+    else cur[0] = fma(mu2, prev[0], (b >= 2) ? c22 * (double)(b - 1) * prev2[0] : 0.0);
+#pragma unroll
+    for (int a = 0; a + 1 < M - b; ++a) {
+      double v = mu1 * cur[a];
+      if (a >= 1) v = fma(c11 * (double)a, cur[a - 1], v);
+      if (b >= 1) v = fma(c12 * (double)b, prev[a], v);
+      cur[a + 1] = v;
+    }
+#pragma unroll
+    for (int a = 0; a < M - b; ++a) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      acc[(a + b) * (a + b + 1) / 2 + a] = fma(wgt, cur[a], acc[(a + b) * (a + b + 1) / 2 + a]);
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) { prev2[a] = prev[a]; prev[a] = cur[a]; }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P) {
+  using D = NdDims<N>;
+  constexpr int S = D::S, SS = D::SS, Z = D::Z, M = D::M;
+  extern __shared__ double smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kNdWarps + warp;
+  if (b >= P.B) return;
+  double* sm = smem_all + warp * (D::kDoubles + D::kInts / 2);
+  int* si = reinterpret_cast<int*>(sm + D::kDoubles);
+  double* ms = sm;
+  double* wts = sm + Z + 5 * SS;
+  double* lam = wts + SS;
+
+  for (int e = lane; e < Z; e += 32) ms[e] = __ldg(P.ms0 + b * P.ms0_stride + e);
+  double mean1 = 0.0, mean2 = 0.0;
+  if (P.mode == MFS_MODE_CENTRAL) {
+    mean1 = __ldg(P.mean0 + b * P.mean0_stride);
+    mean2 = __ldg(P.mean0 + b * P.mean0_stride + 1);
+  }
+  double tp[5], mp[3];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tp[k] = __ldg(P.trans_params + b * P.trans_param_stride + k);
+  mp[0] = __ldg(P.meas_params + b * P.meas_param_stride);
+  mp[1] = __ldg(P.meas_params + b * P.meas_param_stride + 1);
+  mp[2] = 1.0 / mp[0];
+  __syncwarp();
+
+  // The graded-lex position of (a, b) is (a+b)(a+b+1)/2 + a for d = 2; the host verifies that the tables it was given
+  // (multi_indices, inds) are in that order, so the accumulators below can use compile-time positions.
+  double nell = 0.0;
+  int status = -1, reason = 0;
+  int64_t t = 0;
+  for (; t < P.T; ++t) {
+    const double y = (double)__ldg(P.ys + b * P.T + t);
+    // ---------------- prediction ----------------
+    int why = quadrature_nd<N>(P, sm, si, lane);
+    if (why) { status = (int)t; reason = why; break; }
+    double acc[Z];
+    if (P.mode == MFS_MODE_CENTRAL) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int e = lane; e < SS; e += 32) {
+        double m1, m2, c11, c12, c22;
+        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S] + mean1, lam[S + e % S] + mean2, P.dt, tp, m1, m2, c11, c12, c22);
+        s1 = fma(wts[e], m1, s1);
+        s2 = fma(wts[e], m2, s2);
+      }
+      const double nm1 = warp_sum(s1), nm2 = warp_sum(s2);
+      // nodes still refer to the old mean; keep both
+#pragma unroll
+      for (int p = 0; p < Z; ++p) acc[p] = 0.0;
+      for (int e = lane; e < SS; e += 32) {
+        double m1, m2, c11, c12, c22;
+        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S] + mean1, lam[S + e % S] + mean2, P.dt, tp, m1, m2, c11, c12, c22);
+        accumulate_gaussian_moments<N>(wts[e], m1 - nm1, m2 - nm2, c11, c12, c22, acc);
+      }
+      mean1 = nm1;
+      mean2 = nm2;
+    } else {
+#pragma unroll
+      for (int p = 0; p < Z; ++p) acc[p] = 0.0;
+      for (int e = lane; e < SS; e += 32) {
+        double m1, m2, c11, c12, c22;
+        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S], lam[S + e % S], P.dt, tp, m1, m2, c11, c12, c22);
+        accumulate_gaussian_moments<N>(wts[e], m1, m2, c11, c12, c22, acc);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < Z; ++p) {
+      const double v = warp_sum(acc[p]);
+      if (lane == 0) ms[p] = v;
+    }
+    __syncwarp();
+    // ---------------- update ----------------
+    why = quadrature_nd<N>(P, sm, si, lane);
+    if (why) { status = (int)t; reason = why + 4; break; }
+    MeasStep st;
+    st.y = y;
+    st.c0 = 0.0;
+    double cc = 0.0, u1 = 0.0, u2 = 0.0;
+    for (int e = lane; e < SS; e += 32) {
+      const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
+      const double lik = measurement_pdf(P.meas_id, st, P.obs_dim == 0 ? x1 : x2, mp);
+      const double u = wts[e] * lik;
+      wts[e] = u;                 // keep w * likelihood for the moment pass
+      cc += u;
+      u1 = fma(u, x1, u1);
+      u2 = fma(u, x2, u2);
+    }
+    cc = warp_sum(cc);
+    u1 = warp_sum(u1);
+    u2 = warp_sum(u2);
+    const double cinv = 1.0 / cc;
+    double c1 = 0.0, c2 = 0.0;     // centre of the posterior moments
+    if (P.mode == MFS_MODE_CENTRAL) { c1 = u1 * cinv; c2 = u2 * cinv; }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < Z; ++p) acc[p] = 0.0;
+    for (int e = lane; e < SS; e += 32) {
+      const double d1 = lam[e / S] + mean1 - c1, d2 = lam[S + e % S] + mean2 - c2;
+      double pa[M];
+      pa[0] = 1.0;
+#pragma unroll
+      for (int a = 1; a < M; ++a) pa[a] = pa[a - 1] * d1;
+      double pb = wts[e];
+#pragma unroll
+      for (int bb = 0; bb < M; ++bb) {
+#pragma unroll
+        for (int a = 0; a < M - bb; ++a) acc[(a + bb) * (a + bb + 1) / 2 + a] = fma(pb, pa[a], acc[(a + bb) * (a + bb + 1) / 2 + a]);
+        pb *= d2;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < Z; ++p) {
+      const double v = warp_sum(acc[p]) * cinv;
+      if (lane == 0) ms[p] = v;
+    }
+    if (P.mode == MFS_MODE_CENTRAL) { mean1 = c1; mean2 = c2; }
+    nell -= log(cc);
+    __syncwarp();
+    if (P.out_mode == MFS_OUT_FULL) {
+      double* o = P.ms_out + (b * P.T + t) * Z;
+      for (int e = lane; e < Z; e += 32) o[e] = ms[e];
+      if (P.mode == MFS_MODE_CENTRAL && lane == 0) {
+        P.mean_out[(b * P.T + t) * 2] = mean1;
+        P.mean_out[(b * P.T + t) * 2 + 1] = mean2;
+      }
+    }
+  }
+  if (status >= 0) {
+    const double qnan = nan("");
+    nell = qnan; mean1 = qnan; mean2 = qnan;
+    __syncwarp();
+    for (int e = lane; e < Z; e += 32) ms[e] = qnan;
+    __syncwarp();
+    if (P.out_mode == MFS_OUT_FULL) {
+      for (; t < P.T; ++t) {
+        double* o = P.ms_out + (b * P.T + t) * Z;
+        for (int e = lane; e < Z; e += 32) o[e] = qnan;
+        if (P.mode == MFS_MODE_CENTRAL && lane == 0) {
+          P.mean_out[(b * P.T + t) * 2] = qnan;
+          P.mean_out[(b * P.T + t) * 2 + 1] = qnan;
+        }
+      }
+    }
+  }
+  if (P.out_mode == MFS_OUT_LAST) {
+    for (int e = lane; e < Z; e += 32) P.ms_out[b * Z + e] = ms[e];
+    if (P.mode == MFS_MODE_CENTRAL && lane == 0) { P.mean_out[b * 2] = mean1; P.mean_out[b * 2 + 1] = mean2; }
+  }
+  if (lane == 0) {
+    P.nell_out[b] = nell;
+#ifdef MFS_ND_DEBUG_REASON
+    if (status >= 0) status |= reason << 24;
+#endif
+    (void)reason;
+    if (P.status_out) P.status_out[b] = status;
+  }
+}
+
+template <int N>
+cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream);
+
+}  // namespace mfs

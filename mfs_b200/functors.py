@@ -51,6 +51,37 @@ def linear_drift(a) -> Drift:
 
 
 @dataclass(frozen=True, eq=False)
+class DriftND:
+    """d-dimensional drift.  Registered: 'lotka_volterra' x * (x[::-1] * [-beta, delta] + [alpha, -gamma])
+    (``mfs/multi_dims/ss_models.py:55-56``), params (alpha, beta, delta, gamma)."""
+    name: str
+    params: Tuple = ()
+
+    def __post_init__(self):
+        if self.name not in ('lotka_volterra',):
+            raise ValueError(f'unknown d-dimensional drift {self.name!r}; registered: lotka_volterra')
+
+
+@dataclass(frozen=True, eq=False)
+class DispersionND:
+    """d-dimensional dispersion.  Registered: 'proportional' diag(sigma * x) (``ss_models.py:58-59``), params (sigma,)."""
+    name: str
+    params: Tuple = ()
+
+    def __post_init__(self):
+        if self.name not in ('proportional',):
+            raise ValueError(f'unknown d-dimensional dispersion {self.name!r}; registered: proportional')
+
+
+def lotka_volterra_drift(alpha, beta, delta, gamma) -> DriftND:
+    return DriftND('lotka_volterra', (alpha, beta, delta, gamma))
+
+
+def proportional_dispersion(sigma) -> DispersionND:
+    return DispersionND('proportional', (sigma,))
+
+
+@dataclass(frozen=True, eq=False)
 class TransitionSpec:
     family: str          # 'tme' | 'tme_normal' | 'euler' | 'normal_affine'
     drift: Drift
@@ -106,15 +137,17 @@ def gaussian(h=1., r=1.) -> MeasurementFunctor:
     return MeasurementFunctor('gaussian', (h, r))
 
 
-def pack_params(params, batch_shape) -> Tuple[np.ndarray, int]:
-    """Pack up to MAX_PARAMS scalars/arrays into a (B or 1, MAX_PARAMS) float64 table; returns (table, stride)."""
+def pack_params(params, batch_shape, width: int = None) -> Tuple[np.ndarray, int]:
+    """Pack scalars/arrays into a (B or 1, width) float64 table (width = MAX_PARAMS by default); returns
+    (table, stride)."""
+    width = width or _lib.MAX_PARAMS
     B = int(np.prod(batch_shape)) if len(batch_shape) else 1
     per_filter = any(np.ndim(p) > 0 for p in params)
     rows = B if per_filter else 1
-    table = np.zeros((rows, _lib.MAX_PARAMS), dtype=np.float64)
+    table = np.zeros((rows, width), dtype=np.float64)
     for k, p in enumerate(params):
         if np.ndim(p) > 0:
             table[:, k] = np.broadcast_to(np.asarray(p, dtype=np.float64), batch_shape).reshape(-1)
         else:
             table[:, k] = float(p)
-    return table, (_lib.MAX_PARAMS if per_filter else 0)
+    return table, (width if per_filter else 0)

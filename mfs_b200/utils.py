@@ -38,3 +38,31 @@ class GaussianSum1D(NamedTuple):
         scms = cms / np.sqrt(variance) ** np.arange(2 * N)
         return cls(means=means, variances=variances, weights=weights, mean=centre, variance=variance,
                    rms=rms, cms=cms, scms=scms)
+
+
+class GaussianSumND(NamedTuple):
+    """Multidimensional Gaussian-sum distribution (``mfs/utils.py:77-131``); ``new`` computes rms / cms."""
+    d: int
+    means: np.ndarray
+    covs: np.ndarray
+    weights: np.ndarray
+    mean: np.ndarray
+    cov: np.ndarray
+    rms: np.ndarray
+    cms: np.ndarray
+
+    def sampler(self, rng: np.random.Generator, n: int):
+        cs = rng.choice(self.means.shape[0], (n,), p=self.weights)
+        chol = np.linalg.cholesky(self.covs)
+        return self.means[cs] + np.einsum('nij,nj->ni', chol[cs], rng.standard_normal((n, self.d)))
+
+    @classmethod
+    def new(cls, means, covs, weights, multi_indices):
+        from .multi_dims.moments import _gaussian_product_moments
+        means, covs, weights = (np.asarray(a, dtype=np.float64) for a in (means, covs, weights))
+        d = means.shape[1]
+        centre = np.sum(means * weights[:, None], axis=0)
+        cov = sum(w * (c + np.outer(m, m)) for m, c, w in zip(means, covs, weights)) - np.outer(centre, centre)
+        rms = sum(w * _gaussian_product_moments(m, c, multi_indices) for m, c, w in zip(means, covs, weights))
+        cms = sum(w * _gaussian_product_moments(m - centre, c, multi_indices) for m, c, w in zip(means, covs, weights))
+        return cls(d=d, means=means, covs=covs, weights=weights, mean=centre, cov=cov, rms=rms, cms=cms)
