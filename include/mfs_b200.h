@@ -156,6 +156,52 @@ typedef struct mfs_filternd_args {
 /* Enqueue B two-dimensional filters x T steps on `stream` (one warp per filter). */
 int mfs_filter_nd(const mfs_filternd_args* a, void* stream);
 
+/* ---- brute-force grid filter (mfs/classical_filters_smoothers/brute_force.py:26-136) ---------------------------------
+ * B measurement records filtered on ONE shared spatial grid xs[n].  pred_method: brute_force.py:50-58.  The 'chapman'
+ * methods run every integration sub-step as an FP64 tensor-core GEMM  S' = S Pw^T  (S: [B][n] densities, Pw[i][j] =
+ * N(x_i; m_j, s_j) * trapezoid weight_j); 'kolmogorov' is the explicit finite-difference Euler scheme.
+ * Drift functor + constant dispersion as in mfs_filter1d_args; trans_params are shared by all filters (one operator).
+ * Device pointers; the caller owns the workspace (size from mfs_brute_force_workspace_bytes). */
+enum { MFS_BF_CHAPMAN_EULER = 0, MFS_BF_CHAPMAN_TME = 1, MFS_BF_KOLMOGOROV = 2 };
+
+typedef struct mfs_brute_force_args {
+  int32_t abi_version;
+  int32_t pred_method;        /* MFS_BF_* */
+  int32_t tme_order;          /* 1..3, 'chapman-tme-<order>' */
+  int32_t integration_steps;  /* sub-steps between two measurements (>= 1) */
+  int32_t n_grid;             /* n >= 3 */
+  int32_t drift_id;           /* MFS_DRIFT_* */
+  int32_t meas_id;            /* MFS_MEAS_* */
+  int32_t ys_dtype;           /* MFS_YS_* */
+  int64_t B, T;
+  double dt;                  /* time between two measurements */
+  double dispersion;
+  const double* trans_params; /* [MFS_MAX_PARAMS] */
+  const double* meas_params;  /* [B|1][MFS_MAX_PARAMS] */
+  int64_t meas_param_stride;
+  const double* xs;           /* [n] grid (evenly spaced for 'kolmogorov') */
+  const double* init_ps;      /* [B|1][n] initial density values */
+  int64_t init_ps_stride;
+  const void* ys;             /* y[b][t] at ys + b*ys_stride_b + t*ys_stride_t */
+  int64_t ys_stride_b, ys_stride_t;
+  int32_t out_mode;           /* MFS_OUT_FULL: pdfs_out[B][T][n]; MFS_OUT_LAST: pdfs_out[B][n] */
+  int32_t reserved0;
+  double* pdfs_out;
+  double* nell_out;           /* optional [B]: -sum_t log trapz(p(y_t|x) p(x|y_{1:t-1})) (by-product; may be NULL) */
+  void* workspace;
+  int64_t workspace_bytes;
+} mfs_brute_force_args;
+
+/* Workspace size in bytes for mfs_brute_force (-1 for invalid arguments). */
+int64_t mfs_brute_force_workspace_bytes(int32_t n_grid, int64_t B, int32_t pred_method);
+
+/* Enqueue the grid filter on `stream`.  Replaces jax.jit(brute_force_filter)(grid, ys) per trajectory
+ * (dardel/benes_bernoulli/brute_force.py:51-55, 74). */
+int mfs_brute_force(const mfs_brute_force_args* a, void* stream);
+
+/* FP64 tensor-pipe (DMMA m8n8k4) throughput micro-benchmark: the roofline denominator of the grid-filter GEMM. */
+int mfs_dmma_peak(int device, int32_t iters, double* flops, double* ms);
+
 /* ABI version of the loaded library. */
 int mfs_abi_version(void);
 

@@ -64,8 +64,27 @@ class FilterNdArgs(ctypes.Structure):
     ]
 
 
+class BruteForceArgs(ctypes.Structure):
+    """Mirror of ``mfs_brute_force_args``."""
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('pred_method', ctypes.c_int32), ('tme_order', ctypes.c_int32),
+        ('integration_steps', ctypes.c_int32), ('n_grid', ctypes.c_int32), ('drift_id', ctypes.c_int32),
+        ('meas_id', ctypes.c_int32), ('ys_dtype', ctypes.c_int32),
+        ('B', ctypes.c_int64), ('T', ctypes.c_int64), ('dt', ctypes.c_double), ('dispersion', ctypes.c_double),
+        ('trans_params', ctypes.c_void_p), ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
+        ('xs', ctypes.c_void_p), ('init_ps', ctypes.c_void_p), ('init_ps_stride', ctypes.c_int64),
+        ('ys', ctypes.c_void_p), ('ys_stride_b', ctypes.c_int64), ('ys_stride_t', ctypes.c_int64),
+        ('out_mode', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('pdfs_out', ctypes.c_void_p), ('nell_out', ctypes.c_void_p),
+        ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
+    ]
+
+
+BF_METHOD = {'chapman-euler': 0, 'chapman-tme': 1, 'kolmogorov': 2}
+
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
-           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd')
+           'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
+           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak')
 
 _lib = None
 _lock = threading.Lock()
@@ -113,6 +132,13 @@ def lib() -> ctypes.CDLL:
         L.mfs_moment_quadrature_1d.restype = ctypes.c_int
         L.mfs_filter_nd.argtypes = [ctypes.POINTER(FilterNdArgs), ctypes.c_void_p]
         L.mfs_filter_nd.restype = ctypes.c_int
+        L.mfs_brute_force.argtypes = [ctypes.POINTER(BruteForceArgs), ctypes.c_void_p]
+        L.mfs_brute_force.restype = ctypes.c_int
+        L.mfs_brute_force_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32]
+        L.mfs_brute_force_workspace_bytes.restype = ctypes.c_int64
+        L.mfs_dmma_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]
+        L.mfs_dmma_peak.restype = ctypes.c_int
         L.mfs_launch_count.restype = ctypes.c_int64
         L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]
@@ -141,4 +167,12 @@ def fp64_peak(device: int = 0, iters: int = 4096):
     """Measured FP64 FMA throughput (FLOP/s) of ``device``; the roofline denominator of the filter kernels."""
     flops, ms = ctypes.c_double(), ctypes.c_double()
     check(lib().mfs_fp64_peak(device, iters, ctypes.byref(flops), ctypes.byref(ms)))
+    return flops.value, ms.value
+
+
+def dmma_peak(device: int = 0, iters: int = 4096):
+    """Measured FP64 tensor-pipe (DMMA m8n8k4) throughput (FLOP/s) of ``device``: roofline denominator of the
+    grid-filter GEMM."""
+    flops, ms = ctypes.c_double(), ctypes.c_double()
+    check(lib().mfs_dmma_peak(device, iters, ctypes.byref(flops), ctypes.byref(ms)))
     return flops.value, ms.value

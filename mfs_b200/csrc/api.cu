@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "common.h"
 #include "filter1d.cuh"
 #include "filter_nd.cuh"
 
@@ -15,7 +16,9 @@ namespace mfs {
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 
-static int fail(const char* fmt, ...) {
+void count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int fail(const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);

@@ -17,6 +17,7 @@ reference's code, unmodified, from where it lies:
   mfs/multi_dims/multi_indices.py   (pure NumPy)          -> golden_multi_indices.npz
   mfs/multi_dims/moments.py  Kan--Magnus NumPy branches   -> golden_kan_moments.npz
   mfs/multi_dims/quadratures.py, filtering.py, ss_models.py (prey_predator), utils.GaussianSumND -> golden_nd.npz
+  mfs/classical_filters_smoothers/brute_force.py  brute_force_filter -> golden_brute_force.npz
 
 The third-party ``tme`` package is absent, so fixtures whose transition moments are TME expansions take those
 callables from ``oracle/mfs_oracle.py`` (definition-driven restatement) and are labelled ``*_tme*``: they pin the
@@ -277,12 +278,74 @@ def golden_nd():
     print('golden_nd.npz')
 
 
+def golden_brute_force():
+    """mfs/classical_filters_smoothers/brute_force.py executed on the shim.  'chapman-euler' and 'kolmogorov' are 100 %
+    reference code (jax.grad of the shim = complex-step derivative, exact to rounding for analytic drifts); for
+    'chapman-tme-k' the absent third-party ``tme.mean_and_cov`` is the oracle's definition-driven restatement."""
+    import jax
+    import tme.base_jax as tme_base
+    from mfs.classical_filters_smoothers.brute_force import brute_force_filter
+    from jax.scipy.stats import norm
+
+    def grad(f):
+        def df(x):
+            h = 1e-30
+            return np.imag(np.asarray(f(np.asarray(x, dtype=np.complex128) + 1j * h))) / h
+        return df
+
+    jax.grad = grad
+    state = {}
+
+    def mean_and_cov(x, ddt, drift, dispersion, order):
+        _, mv = O.tme_1d(state['drift'], state['params'], state['b'], float(ddt), order, 2)
+        m, v = mv(np.asarray(x))
+        return m, v.reshape(1, 1)
+
+    tme_base.mean_and_cov = mean_and_cov
+    out = {}
+    rng = np.random.Generator(np.random.PCG64(672))
+    # (1) Benes--Bernoulli on a 200-point grid
+    dt, T, ts, init_cond, drift, dispersion, logistic, pmf, _ = benes_bernoulli(3)
+    state.update(drift='benes', params=(), b=1.)
+    xs = np.linspace(-4., 4., 200)
+    ys = synth_benes_bernoulli(rng, 6, dt, 3)
+    init_ps = np.asarray(init_cond.pdf(jnp.asarray(xs)))
+    out['benes/xs'], out['benes/ys'], out['benes/init_ps'], out['benes/dt'] = xs, ys, init_ps, dt
+    for method, steps in (('chapman-euler', 5), ('chapman-tme-2', 5), ('chapman-tme-3', 5), ('chapman-tme-3', 1),
+                          ('kolmogorov', 20)):
+        for k in range(ys.shape[0]):
+            pss = brute_force_filter(drift, dispersion, pmf, jnp.asarray(init_ps), jnp.asarray(xs), jnp.asarray(ys[k]),
+                                     dt, integration_steps=steps, pred_method=method)
+            out[f'benes/{method}/{steps}/{k}'] = np.asarray(pss)
+    # (2) OU + Gaussian likelihood, the setting of tests/test_classical_filters_smoothers.py:127-160 on a smaller grid
+    import math
+    ell, sigma, r2 = 1., 0.5, 0.1
+    b = math.sqrt(2) * sigma / math.sqrt(ell)
+    state.update(drift='ou', params=(ell,), b=b)
+    xs = np.linspace(-5., 5., 300)
+    T = 10
+    traj = np.cumsum(0.1 * rng.standard_normal(T))
+    ys = traj + math.sqrt(r2) * rng.standard_normal(T)
+    init_ps = np.asarray(norm.pdf(xs, 0., sigma))
+    out['ou/xs'], out['ou/ys'], out['ou/init_ps'], out['ou/dt'] = xs, ys, init_ps, 1e-2
+    out['ou/ell'], out['ou/sigma'], out['ou/r2'] = ell, sigma, r2
+    for method, steps in (('chapman-euler', 4), ('chapman-tme-3', 4), ('kolmogorov', 20)):
+        pss = brute_force_filter(lambda u: -1 / ell * u, lambda _: b, lambda y, x: norm.pdf(y, x, math.sqrt(r2)),
+                                 jnp.asarray(init_ps), jnp.asarray(xs), jnp.asarray(ys), 1e-2,
+                                 integration_steps=steps, pred_method=method)
+        out[f'ou/{method}/{steps}'] = np.asarray(pss)
+    np.savez_compressed(os.path.join(HERE, 'golden_brute_force.npz'), **out)
+    print('golden_brute_force.npz')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd']
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force']
     if 'multi_indices' in which:
         golden_multi_indices()
     if 'nd' in which:
         golden_nd()
+    if 'brute_force' in which:
+        golden_brute_force()
     if 'quadrature' in which:
         golden_quadrature_1d()
     if 'conversions' in which:
