@@ -102,8 +102,13 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
       for (int q = 0; q < 2 * N; ++q) {
         s0[q] = fma(w[i], pw, s0[q]);
         s1[q] = fma(wt, pw, s1[q]);
-        pw = pw * delta * (1.0 / (q + 1));
+        pw *= delta;
       }
+    }
+    {  // s[q] /= q!  (the TME combination below works on delta^q / q!)
+      double rf = 1.0;
+#pragma unroll
+      for (int q = 2; q < 2 * N; ++q) { rf *= 1.0 / q; s0[q] *= rf; s1[q] *= rf; }
     }
     const double dt2 = dt * dt, dt3 = dt2 * dt;
     const bool o2 = P.tme_order >= 2, o3 = P.tme_order >= 3;
@@ -262,8 +267,12 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
     bool ok = true;
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && have_atoms) ok = hankel_is_pd<N>(ms);
-      else ok = moment_quadrature<N>(ms, mean, scale, w, x);
+      {
+        // ONE instance of the moments -> Jacobi code; with carried atoms only its pivot test is used
+        double dj[N], ej[N];
+        ok = jacobi_from_moments<N, false>(ms, dj, ej);
+        if (ok && !(phase == 0 && have_atoms)) ok = jacobi_to_rule<N>(dj, ej, mean, scale, w, x);
+      }
       if (!ok) break;
       if (phase == 0) {
         predict<N, MODE, KIND>(P, tp, w, x, ms, mean, scale);
