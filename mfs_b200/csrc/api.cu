@@ -87,7 +87,6 @@ static int validate(const mfs_filter1d_args* a) {
   if (a->mode == MFS_MODE_SCALED && a->trans_id != MFS_TRANS_TME)
     return fail("scaled central moments are only offered with the TME family: the reference's scaled Normal/Euler "
                 "factories divide every order by prod(scale**k) (mfs/one_dim/moments.py:205,243)");
-  if (a->stable) return fail("stable=True (LDL completion, mfs/utils.py:526-538) is not implemented in this build");
   if (!(a->dt > 0.0)) return fail("dt must be > 0");
   if (a->B == 0) return 0;
   if (!a->ms0 || !a->trans_params || !a->meas_params || !a->nell_out) return fail("ms0 / trans_params / meas_params / nell_out must not be NULL");
@@ -139,14 +138,14 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
 template <int N>
 __global__ void __launch_bounds__(kBlock) quadrature_kernel(int64_t B, const double* __restrict__ ms,
                                                             const double* __restrict__ mean,
-                                                            const double* __restrict__ scale, int sort_nodes,
+                                                            const double* __restrict__ scale, int sort_nodes, int ldl,
                                                             double* __restrict__ weights, double* __restrict__ nodes) {
   const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (b >= B) return;
   double m[2 * N], w[N], x[N];
 #pragma unroll
   for (int p = 0; p < 2 * N; ++p) m[p] = ms[b * 2 * N + p];
-  const bool ok = moment_quadrature<N>(m, mean ? mean[b] : 0.0, scale ? scale[b] : 1.0, w, x);
+  const bool ok = moment_quadrature<N>(m, mean ? mean[b] : 0.0, scale ? scale[b] : 1.0, w, x, ldl != 0);
   if (!ok) {
 #pragma unroll
     for (int i = 0; i < N; ++i) { w[i] = nan(""); x[i] = nan(""); }
@@ -169,9 +168,9 @@ __global__ void __launch_bounds__(kBlock) quadrature_kernel(int64_t B, const dou
 
 template <int N>
 static cudaError_t launch_quadrature(int64_t B, const double* ms, const double* mean, const double* scale, int sort,
-                                     double* w, double* x, cudaStream_t s) {
+                                     int ldl, double* w, double* x, cudaStream_t s) {
   const unsigned grid = (unsigned)((B + kBlock - 1) / kBlock);
-  quadrature_kernel<N><<<grid, kBlock, 0, s>>>(B, ms, mean, scale, sort, w, x);
+  quadrature_kernel<N><<<grid, kBlock, 0, s>>>(B, ms, mean, scale, sort, ldl, w, x);
   return cudaGetLastError();
 }
 
@@ -346,14 +345,13 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
 int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
                              int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream) {
   if (N < 1 || N > MFS_MAX_N) return fail("N=%d outside [1, %d]", N, MFS_MAX_N);
-  if (ldl) return fail("ldl=True is not implemented in this build");
   if (B < 0) return fail("negative B");
   if (B == 0) return 0;
   if (!ms || !weights || !nodes) return fail("NULL pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaErrorInvalidValue;
   switch (N) {
-#define MFS_CASE(n) case n: e = launch_quadrature<n>(B, ms, mean, scale, sort_nodes, weights, nodes, s); break;
+#define MFS_CASE(n) case n: e = launch_quadrature<n>(B, ms, mean, scale, sort_nodes, ldl, weights, nodes, s); break;
     MFS_CASE(1) MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
     MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
 #undef MFS_CASE

@@ -271,7 +271,12 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
         // ONE instance of the moments -> Jacobi code; with carried atoms only its pivot test is used
         double dj[N], ej[N];
         ok = jacobi_from_moments<N, false>(ms, dj, ej);
-        if (ok && !(phase == 0 && have_atoms)) ok = jacobi_to_rule<N>(dj, ej, mean, scale, w, x);
+        if (ok) {
+          if (!(phase == 0 && have_atoms)) ok = jacobi_to_rule<N>(dj, ej, mean, scale, w, x);
+        } else if (P.stable) {
+          // stable=True: a non-positive pivot is not a failure but the LDL completion of mfs/utils.py:526-538
+          ok = moment_quadrature_stable_fallback<N>(ms, mean, scale, w, x);
+        }
       }
       if (!ok) break;
       if (phase == 0) {
@@ -279,7 +284,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
       } else {
         const double cc = update<N, MODE>(P, mp, y, w, x, ms, mean, scale);
         nell -= log(cc);
-        have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE);
+        // stable=True always re-derives the prediction quadrature (its LDL completion is defined on the moments)
+        have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE) && !P.stable;
       }
     }
     if (!ok) { status = (int)t; break; }

@@ -104,8 +104,11 @@ def moment_quadrature(ms: np.ndarray, mean: float = 0., scale: float = 1., sort_
     if not (np.all(np.isfinite(R)) and np.all(np.isfinite(H))):
         return np.full((n,), np.nan), np.full((n,), np.nan)
     with np.errstate(all='ignore'):
-        Y = scipy.linalg.solve_triangular(R, H, lower=True, check_finite=False)        # R^-1 H
-        K = scipy.linalg.solve_triangular(R, Y.T, lower=True, check_finite=False).T   # (R^-1 H) R^-T   :128-129
+        try:
+            Y = scipy.linalg.solve_triangular(R, H, lower=True, check_finite=False)        # R^-1 H
+            K = scipy.linalg.solve_triangular(R, Y.T, lower=True, check_finite=False).T   # (R^-1 H) R^-T   :128-129
+        except scipy.linalg.LinAlgError:     # exactly singular factor: XLA's trsm divides by zero -> inf/NaN
+            return np.full((n,), np.nan), np.full((n,), np.nan)
     if not np.all(np.isfinite(K)):
         return np.full((n,), np.nan), np.full((n,), np.nan)
     K = 0.5 * (K + K.T)                                                     # eigh(symmetrize_input=True)

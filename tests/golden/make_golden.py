@@ -18,6 +18,7 @@ reference's code, unmodified, from where it lies:
   mfs/multi_dims/moments.py  Kan--Magnus NumPy branches   -> golden_kan_moments.npz
   mfs/multi_dims/quadratures.py, filtering.py, ss_models.py (prey_predator), utils.GaussianSumND -> golden_nd.npz
   mfs/classical_filters_smoothers/brute_force.py  brute_force_filter -> golden_brute_force.npz
+  mfs/utils.py ldl_chol through moment_quadrature(ldl=True) / moment_filter_rms(stable=True) -> golden_stable.npz
 
 The third-party ``tme`` package is absent, so fixtures whose transition moments are TME expansions take those
 callables from ``oracle/mfs_oracle.py`` (definition-driven restatement) and are labelled ``*_tme*``: they pin the
@@ -338,14 +339,50 @@ def golden_brute_force():
     print('golden_brute_force.npz')
 
 
+def golden_stable():
+    """`stable=True` / `ldl=True` on moment sequences whose Hankel matrix has NEGATIVE LDL pivots (the case where
+    mfs/utils.py:538 substitutes eps and K stops being tridiagonal), 100 % reference code:
+    quadratures (quadtures.py:127 with ldl=True) and an Euler--Maruyama raw-moment filter started from a non-PD
+    initial sequence (filtering.py:73-86 with stable=True)."""
+    out = {}
+    cases = {'n4': np.array([1., 0., 1., 0., 0.5, 0., 3., 0.])}
+    for N in (3, 5, 8):
+        ic = GaussianSum1D.new(means=jnp.array([-0.5, 0.5]), variances=jnp.array([0.05, 0.05]),
+                               weights=jnp.array([0.5, 0.5]), N=N)
+        bad = np.asarray(ic.rms).copy()
+        bad[2 * (N // 2)] *= 0.5          # breaks a middle pivot
+        cases[f'mix{N}'] = bad
+        bad2 = np.asarray(ic.rms).copy()
+        bad2[2 * N - 2] *= 0.2            # breaks the last pivot only
+        cases[f'mix{N}_last'] = bad2
+    for name, ms in cases.items():
+        w, x = moment_quadrature(jnp.asarray(ms), 0.3, 1.7, sort_nodes=True, ldl=True)
+        out[f'quad/{name}/ms'], out[f'quad/{name}/weights'], out[f'quad/{name}/nodes'] = ms, np.asarray(w), np.asarray(x)
+    rng = np.random.Generator(np.random.PCG64(673))
+    N = 5
+    dt, T, ts, init_cond, drift, dispersion, logistic, pmf, _ = benes_bernoulli(N)
+    ys_all = synth_benes_bernoulli(rng, 30, dt, 2)
+    e_rms, e_cms, e_scms, e_mean, e_mean_var = sde_cond_moments_euler(drift, dispersion, dt, N)
+    bad = np.asarray(init_cond.rms).copy()
+    bad[4] *= 0.9          # one negative LDL pivot at step 0; the run stays finite
+    out['filter/ys'], out['filter/rms0'], out['filter/dt'] = ys_all, bad, dt
+    for k in range(2):
+        rmss, nell = moment_filter_rms(e_rms, pmf, jnp.asarray(bad), jnp.asarray(ys_all[k]), stable=True)
+        out[f'filter/{k}/rmss'], out[f'filter/{k}/nell'] = np.asarray(rmss), float(nell)
+    np.savez_compressed(os.path.join(HERE, 'golden_stable.npz'), **out)
+    print('golden_stable.npz', {k: out[k] for k in out if k.endswith('nell')})
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force']
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force', 'stable']
     if 'multi_indices' in which:
         golden_multi_indices()
     if 'nd' in which:
         golden_nd()
     if 'brute_force' in which:
         golden_brute_force()
+    if 'stable' in which:
+        golden_stable()
     if 'quadrature' in which:
         golden_quadrature_1d()
     if 'conversions' in which:

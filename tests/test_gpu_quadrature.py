@@ -55,5 +55,23 @@ def test_reference_known_answers_batched():
         w, x = moment_quadrature(mu)
         for p in range(2 * nn):
             np.testing.assert_allclose(np.dot(w, x ** p), mu[p], rtol=1e-7)
-    with pytest.raises(_lib.MfsError):
-        moment_quadrature(rms, ldl=True)
+    # ldl=True on a PD sequence is the same rule
+    w1, x1 = moment_quadrature(rms, sort_nodes=True)
+    w2, x2 = moment_quadrature(rms, sort_nodes=True, ldl=True)
+    np.testing.assert_array_equal(w1, w2)
+    np.testing.assert_array_equal(x1, x2)
+
+
+def test_quadrature_ldl_negative_pivots_against_reference_golden():
+    """quadtures.py:127 with ldl=True on Hankel matrices with negative LDL pivots (dense route); weights that the
+    reference itself only resolves to ~1e-17 are compared absolutely."""
+    g = np.load(os.path.join(GOLD, 'golden_stable.npz'))
+    names = sorted({k.split('/')[1] for k in g.files if k.startswith('quad/')})
+    assert len(names) == 7
+    for name in names:
+        w, x = moment_quadrature(g[f'quad/{name}/ms'], 0.3, 1.7, sort_nodes=True, ldl=True)
+        # the eps-substituted pivot puts |K| at ~1e8: any backward-stable eigen-solver (LAPACK in the reference, Jacobi
+        # here) resolves the O(1) nodes and the weights only to ~eps |K|
+        floor = 2e-14 * np.abs(g[f'quad/{name}/nodes']).max() + 1e-10
+        np.testing.assert_allclose(x, g[f'quad/{name}/nodes'], rtol=1e-9, atol=floor)
+        np.testing.assert_allclose(w, g[f'quad/{name}/weights'], rtol=1e-8, atol=floor)
