@@ -134,7 +134,7 @@ typedef struct mfs_filternd_args {
   int32_t N;             /* 2..6 */
   int32_t d;             /* must be 2 */
   int64_t B, T;
-  int32_t trans_id;      /* MFS_TRANS_EULER | MFS_TRANS_TME_NORMAL */
+  int32_t trans_id;      /* MFS_TRANS_EULER | MFS_TRANS_TME_NORMAL | MFS_TRANS_TME (moments.py:414-479) */
   int32_t tme_order;     /* 1..2 */
   int32_t meas_id;
   int32_t obs_dim;

@@ -367,9 +367,9 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
   if (a->d != 2) return fail("only d = 2 is implemented (got d = %d)", a->d);
   if (a->N < 2 || a->N > 6) return fail("N=%d outside [2, 6] for the 2-D filter", a->N);
   if (a->mode != MFS_MODE_RAW && a->mode != MFS_MODE_CENTRAL) return fail("2-D filter: mode must be raw or central");
-  if (a->trans_id != MFS_TRANS_EULER && a->trans_id != MFS_TRANS_TME_NORMAL)
-    return fail("2-D filter: transition must be euler or tme_normal (Lotka--Volterra)");
-  if (a->trans_id == MFS_TRANS_TME_NORMAL && (a->tme_order < 1 || a->tme_order > 2)) return fail("2-D filter: tme_order must be 1 or 2");
+  if (a->trans_id != MFS_TRANS_EULER && a->trans_id != MFS_TRANS_TME_NORMAL && a->trans_id != MFS_TRANS_TME)
+    return fail("2-D filter: transition must be euler, tme_normal or tme (Lotka--Volterra)");
+  if (a->trans_id != MFS_TRANS_EULER && (a->tme_order < 1 || a->tme_order > 2)) return fail("2-D filter: tme_order must be 1 or 2");
   if (a->meas_id != MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) return fail("2-D filter: measurement must be bernoulli_logistic_cubic");
   if (a->obs_dim < 0 || a->obs_dim > 1) return fail("obs_dim must be 0 or 1");
   if (a->B < 0 || a->T < 0) return fail("negative B or T");

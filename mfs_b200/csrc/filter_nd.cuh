@@ -22,7 +22,7 @@ constexpr int kNdWarps = 4;  // warps (filters) per CTA
 
 struct NdArgs {
   int32_t mode;        // MFS_MODE_RAW / MFS_MODE_CENTRAL
-  int32_t trans_id;    // MFS_TRANS_EULER / MFS_TRANS_TME_NORMAL
+  int32_t trans_id;    // MFS_TRANS_EULER / MFS_TRANS_TME_NORMAL / MFS_TRANS_TME
   int32_t tme_order;   // 1 or 2
   int32_t meas_id;     // MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC on x[obs_dim]
   int32_t obs_dim;
@@ -72,6 +72,44 @@ MFS_DEV void lv_mean_cov(int trans_id, int order, double x1, double x2, double d
     c11 = fma(dt * dt * sg2 * x1 * x1, 2.0 * al - 2.0 * be * x2 + 0.5 * sg2, c11);
     c22 = fma(dt * dt * sg2 * x2 * x2, 2.0 * de * x1 - 2.0 * ga + 0.5 * sg2, c22);
     c12 = 0.5 * dt * dt * sg2 * x1 * x2 * (de * x1 - be * x2);
+  }
+}
+
+// TME of the Lotka--Volterra SDE WITHOUT the Normal approximation (sde_cond_moments_tme, mfs/multi_dims/moments.py:414-479;
+// third-party tme.expectation restated from its definition).  With A = a . grad + 1/2 Gamma : Hess,
+// Gamma = diag(sg2 x1^2, sg2 x2^2), any smooth phi satisfies
+//     sum_{r <= order} dt^r / r! A^r phi = sum_{p+q <= 2 order} G[p][q](x) d1^p d2^q phi .
+// A = sum over the four "operator atoms" (i, j, c): (1,0,a1) (0,1,a2) (2,0,Gamma11/2) (0,2,Gamma22/2), and the product
+// rule of a second-order operator, A(c D) = c A D + (A c) D + Gamma11 d1c d1 D + Gamma22 d2c d2 D, gives A^2.
+// Orders 1 and 2.  tools/derive_lv_tme.py prints the same G symbolically; the oracle applies A to every monomial.
+MFS_DEV void lv_tme_operator(int order, double x1, double x2, double dt, const double* p, double (&G)[5][5]) {
+  const double al = p[0], be = p[1], de = p[2], ga = p[3], sg2 = p[4] * p[4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) G[i][j] = 0.0;
+  const double g11 = sg2 * x1 * x1, g22 = sg2 * x2 * x2;
+  const double c[4] = {x1 * (al - be * x2), x2 * (de * x1 - ga), 0.5 * g11, 0.5 * g22};
+  G[0][0] = 1.0;
+  G[1][0] = dt * c[0];
+  G[0][1] = dt * c[1];
+  G[2][0] = dt * c[2];
+  G[0][2] = dt * c[3];
+  if (order >= 2) {
+    const double h = 0.5 * dt * dt;
+    constexpr int oi[4] = {1, 0, 2, 0}, oj[4] = {0, 1, 0, 2};
+    const double d1c[4] = {al - be * x2, de * x2, sg2 * x1, 0.0};
+    const double d2c[4] = {-be * x1, de * x1 - ga, 0.0, sg2 * x2};
+    const double d11c[4] = {0.0, 0.0, sg2, 0.0}, d22c[4] = {0.0, 0.0, 0.0, sg2};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double Ac = c[0] * d1c[u] + c[1] * d2c[u] + c[2] * d11c[u] + c[3] * d22c[u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) G[oi[u] + oi[v]][oj[u] + oj[v]] = fma(h * c[u], c[v], G[oi[u] + oi[v]][oj[u] + oj[v]]);
+      G[oi[u]][oj[u]] = fma(h, Ac, G[oi[u]][oj[u]]);
+      G[oi[u] + 1][oj[u]] = fma(h * g11, d1c[u], G[oi[u] + 1][oj[u]]);
+      G[oi[u]][oj[u] + 1] = fma(h * g22, d2c[u], G[oi[u]][oj[u] + 1]);
+    }
   }
 }
 
@@ -279,6 +317,43 @@ MFS_DEV void accumulate_gaussian_moments(double wgt, double mu1, double mu2, dou
   }
 }
 
+// acc[pos(a, b)] += wgt * sum_{p,q} G[p][q] d1^p d2^q [dl1^a dl2^b]
+//                  = wgt * a! b! * sum_q (sum_p G[p][q] dl1^{a-p}/(a-p)!) dl2^{b-q}/(b-q)!      -- registers only
+template <int N>
+MFS_DEV void accumulate_tme_moments(double wgt, double dl1, double dl2, const double (&G)[5][5],
+                                    double (&acc)[NdDims<N>::Z]) {
+  constexpr int M = 2 * N;
+  double P1[M], P2[M];
+  P1[0] = 1.0;
+  P2[0] = 1.0;
+#pragma unroll
+  for (int a = 1; a < M; ++a) { P1[a] = P1[a - 1] * dl1 * (1.0 / a); P2[a] = P2[a - 1] * dl2 * (1.0 / a); }
+  double fa = wgt;   // wgt * a!
+#pragma unroll
+  for (int a = 0; a < M; ++a) {
+    if (a > 0) fa *= (double)a;
+    double u[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      double v = 0.0;
+#pragma unroll
+      for (int pp = 0; pp + q < 5; ++pp)
+        if (pp <= a) v = fma(G[pp][q], P1[a - pp], v);
+      u[q] = v * fa;
+    }
+    double fb = 1.0;   // b!
+#pragma unroll
+    for (int b = 0; b < M - a; ++b) {
+      if (b > 0) fb *= (double)b;
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (q <= b) t = fma(u[q], P2[b - q], t);
+      acc[(a + b) * (a + b + 1) / 2 + a] = fma(t, fb, acc[(a + b) * (a + b + 1) / 2 + a]);
+    }
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P) {
   using D = NdDims<N>;
@@ -318,11 +393,14 @@ __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P
     int why = quadrature_nd<N>(P, sm, si, lane);
     if (why) { status = (int)t; reason = why; break; }
     double acc[Z];
+    const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
     if (P.mode == MFS_MODE_CENTRAL) {
       double s1 = 0.0, s2 = 0.0;
       for (int e = lane; e < SS; e += 32) {
+        const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
         double m1, m2, c11, c12, c22;
-        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S] + mean1, lam[S + e % S] + mean2, P.dt, tp, m1, m2, c11, c12, c22);
+        // state_cond_mean = tme.expectation(identity): same expansion for both TME factories (moments.py:401-403, 469-471)
+        lv_mean_cov(tme_full ? MFS_TRANS_TME_NORMAL : P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
         s1 = fma(wts[e], m1, s1);
         s2 = fma(wts[e], m2, s2);
       }
@@ -331,9 +409,16 @@ __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P
 #pragma unroll
       for (int p = 0; p < Z; ++p) acc[p] = 0.0;
       for (int e = lane; e < SS; e += 32) {
-        double m1, m2, c11, c12, c22;
-        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S] + mean1, lam[S + e % S] + mean2, P.dt, tp, m1, m2, c11, c12, c22);
-        accumulate_gaussian_moments<N>(wts[e], m1 - nm1, m2 - nm2, c11, c12, c22, acc);
+        const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
+        if (tme_full) {
+          double G[5][5];
+          lv_tme_operator(P.tme_order, x1, x2, P.dt, tp, G);
+          accumulate_tme_moments<N>(wts[e], x1 - nm1, x2 - nm2, G, acc);
+        } else {
+          double m1, m2, c11, c12, c22;
+          lv_mean_cov(P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
+          accumulate_gaussian_moments<N>(wts[e], m1 - nm1, m2 - nm2, c11, c12, c22, acc);
+        }
       }
       mean1 = nm1;
       mean2 = nm2;
@@ -341,9 +426,16 @@ __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P
 #pragma unroll
       for (int p = 0; p < Z; ++p) acc[p] = 0.0;
       for (int e = lane; e < SS; e += 32) {
-        double m1, m2, c11, c12, c22;
-        lv_mean_cov(P.trans_id, P.tme_order, lam[e / S], lam[S + e % S], P.dt, tp, m1, m2, c11, c12, c22);
-        accumulate_gaussian_moments<N>(wts[e], m1, m2, c11, c12, c22, acc);
+        const double x1 = lam[e / S], x2 = lam[S + e % S];
+        if (tme_full) {
+          double G[5][5];
+          lv_tme_operator(P.tme_order, x1, x2, P.dt, tp, G);
+          accumulate_tme_moments<N>(wts[e], x1, x2, G, acc);
+        } else {
+          double m1, m2, c11, c12, c22;
+          lv_mean_cov(P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
+          accumulate_gaussian_moments<N>(wts[e], m1, m2, c11, c12, c22, acc);
+        }
       }
     }
     __syncwarp();

@@ -28,6 +28,9 @@ def _check(fn_and_flag, role):
                         'mfs_b200.multi_dims.moments.sde_cond_moments_*; Python callables cannot run in the kernel.')
     if fn.role != role:
         raise ValueError(f'expected the {role!r} member of the factory tuple, got {fn.role!r}')
+    want = 'multi-index' if fn.spec.family == 'tme' else 'index'      # moments.py:296-337 vs :441-459
+    if flag != want:
+        raise ValueError(f"the {fn.spec.family!r} factory has the {want!r} signature (got flag {flag!r})")
     return fn.spec
 
 

@@ -8,7 +8,7 @@ import numpy as np
 from ..functors import DriftND, DispersionND
 
 __all__ = ['raw_moments_mvn_kan', 'central_moments_mvn_kan', 'sde_cond_moments_euler_maruyama',
-           'sde_cond_moments_tme_normal', 'TransitionSpecND', 'TransitionFunctorND']
+           'sde_cond_moments_tme_normal', 'sde_cond_moments_tme', 'TransitionSpecND', 'TransitionFunctorND']
 
 
 def _gaussian_product_moments(mean, cov, multi_indices):
@@ -49,7 +49,7 @@ def central_moments_mvn_kan(cov, multi_index) -> float:
 
 @dataclass(frozen=True, eq=False)
 class TransitionSpecND:
-    family: str            # 'euler' | 'tme_normal'
+    family: str            # 'euler' | 'tme_normal' | 'tme'
     drift: DriftND
     dispersion: DispersionND
     dt: float
@@ -90,3 +90,11 @@ def sde_cond_moments_tme_normal(drift, dispersion, dt, tme_order, multi_indices)
     if tme_order not in (1, 2):
         raise ValueError('tme_order must be 1 or 2 for the d-dimensional TME-normal functor')
     return _factory('tme_normal', drift, dispersion, dt, tme_order, multi_indices)
+
+
+def sde_cond_moments_tme(drift, dispersion, dt, tme_order):
+    """Mirror of ``mfs/multi_dims/moments.py:414-479`` (TME without the Normal approximation, orders 1 and 2); use with
+    the ``'multi-index'`` signature flag, like the reference (``dardel/prey_predator/mf.py``)."""
+    if tme_order not in (1, 2):
+        raise ValueError('tme_order must be 1 or 2 for the d-dimensional TME functor')
+    return _factory('tme', drift, dispersion, dt, tme_order, None)

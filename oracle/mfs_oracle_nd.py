@@ -261,3 +261,49 @@ def lv_cond_moments(kind, multi_indices, order=2, use_kan=True):
         return out
 
     return (lambda x: moments(x, 0.)), (lambda x, m: moments(x, np.asarray(m))), (lambda x: lv_mean_cov(x, kind, order)[0])
+
+
+@lru_cache(maxsize=None)
+def _lv_tme_moment_fns(order, multi_indices_key):
+    """tme.expectation(phi_n, x, dt, drift, dispersion, order) for phi_n(u) = prod((u - m)^n), every multi-index n
+    (mfs/multi_dims/moments.py:441-459): the generator is applied symbolically to EACH monomial, `order` times."""
+    import sympy as sp
+    x1, x2, m1, m2, dt, al, be, de, ga, sg = sp.symbols('x1 x2 m1 m2 dt alp beta delta gamma sigma', real=True)
+    X = [x1, x2]
+    a = [x1 * (al - be * x2), x2 * (de * x1 - ga)]
+    g = [sg ** 2 * x1 ** 2, sg ** 2 * x2 ** 2]
+
+    def gen(phi):
+        return sum(a[i] * sp.diff(phi, X[i]) + sp.Rational(1, 2) * g[i] * sp.diff(phi, X[i], 2) for i in range(2))
+
+    exprs = []
+    for n in multi_indices_key:
+        cur = (x1 - m1) ** n[0] * (x2 - m2) ** n[1]
+        tot = cur
+        for r in range(1, order + 1):
+            cur = gen(cur)
+            tot = tot + dt ** r / math.factorial(r) * cur
+        exprs.append(tot)
+    return sp.lambdify((x1, x2, m1, m2, dt, al, be, de, ga, sg), exprs, modules='numpy', cse=True)
+
+
+def lv_cond_moments_tme(multi_indices, order=2, p=LV):
+    """(state_cond_raw_moments(x), state_cond_central_moments(x, mean), state_cond_mean(x)) of
+    ``sde_cond_moments_tme`` (moments.py:414-479, 'multi-index' signature) for the LV model."""
+    multi_indices = np.asarray(multi_indices)
+    key = tuple(tuple(int(v) for v in row) for row in multi_indices)
+    fn = _lv_tme_moment_fns(order, key)
+    fn_mean = _lv_tme_moment_fns(order, ((1, 0), (0, 1)))
+
+    def moments(x, shift):
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        shift = np.broadcast_to(np.asarray(shift, dtype=np.float64), (2,))
+        cols = fn(x[:, 0], x[:, 1], shift[0], shift[1], p['dt'], p['alp'], p['beta'], p['delta'], p['gamma'], p['sigma'])
+        return np.stack([np.broadcast_to(np.asarray(c, dtype=np.float64), x.shape[:1]) for c in cols], axis=-1)
+
+    def mean(x):
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        cols = fn_mean(x[:, 0], x[:, 1], 0., 0., p['dt'], p['alp'], p['beta'], p['delta'], p['gamma'], p['sigma'])
+        return np.stack([np.broadcast_to(np.asarray(c, dtype=np.float64), x.shape[:1]) for c in cols], axis=-1)
+
+    return (lambda x: moments(x, 0.)), (lambda x, m: moments(x, m)), mean

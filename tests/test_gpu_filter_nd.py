@@ -95,3 +95,42 @@ def test_nd_errors():
     bad[3] = bad[1] ** 2 - 1e-3
     r, n, st = moment_filter_nd_rms((fam[0], 'index'), pmf, ys, (mis, inds), bad, return_status=True)
     assert np.all(np.isnan(r)) and np.isnan(n) and st == 0
+
+
+@pytest.mark.parametrize('N, order', [(3, 1), (3, 2), (5, 2)])
+def test_tme_without_normal_approximation_against_oracle(N, order):
+    """sde_cond_moments_tme (mfs/multi_dims/moments.py:414-479, 'multi-index' signature; the paper's `tme_2` run):
+    operator-coefficient evaluation on the device vs the oracle applying the generator to every monomial."""
+    from mfs_b200.multi_dims.moments import sde_cond_moments_tme
+    B, T = 4, 10
+    mis = generate_graded_lexico_multi_indices(2, 2 * N - 1, 0)
+    inds = gram_and_hankel_indices_graded_lexico(N, 2)
+    dt, _, ts, gs, drift, dispersion, emission, pmf, simulate = prey_predator(mis)
+    rng = np.random.Generator(np.random.PCG64(676 + N))
+    _, xs, ys = simulate(rng, integration_steps=10, T=T, n=B)
+    fam = sde_cond_moments_tme(drift, dispersion, dt, order)
+    with pytest.raises(ValueError):
+        moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, ys, (mis, inds), gs.cms, gs.mean)
+    cmss, means, nell, status = moment_filter_nd_cms((fam[1], 'multi-index'), fam[3], pmf, torch.from_numpy(ys).cuda(),
+                                                     (mis, inds), gs.cms, gs.mean, return_status=True)
+    f_r, f_c, f_m = ND.lv_cond_moments_tme(mis, order)
+    status = status.cpu().numpy()
+    n_ok = 0
+    for k in range(B):
+        ref_c, ref_m, ref_n = ND.moment_filter_nd_cms(f_c, f_m, ND.lv_measurement_pmf, ys[k], (mis, inds), gs.cms, gs.mean)
+        if not np.isfinite(ref_n) or status[k] >= 0:
+            continue
+        n_ok += 1
+        np.testing.assert_allclose(means[k].cpu().numpy(), ref_m, rtol=1e-9)
+        np.testing.assert_allclose(nell[k].item(), ref_n, rtol=1e-9)
+        scale = np.abs(ref_c[:, 5:6]) ** (mis.sum(axis=1) / 2.)
+        assert np.max(np.abs(cmss[k].cpu().numpy() - ref_c) / np.maximum(np.abs(ref_c), scale)) < 1e-6
+    assert n_ok >= B - 1
+    if N == 3:   # raw moments too
+        rmss, nell_r, st = moment_filter_nd_rms((fam[0], 'multi-index'), pmf, torch.from_numpy(ys).cuda(), (mis, inds),
+                                                gs.rms, return_status=True)
+        for k in range(B):
+            ref_r, ref_n = ND.moment_filter_nd_rms(f_r, ND.lv_measurement_pmf, ys[k], (mis, inds), gs.rms)
+            if np.isfinite(ref_n) and st[k].item() < 0:
+                np.testing.assert_allclose(rmss[k].cpu().numpy(), ref_r, rtol=1e-6)
+                np.testing.assert_allclose(nell_r[k].item(), ref_n, rtol=1e-7)
