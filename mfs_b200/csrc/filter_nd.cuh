@@ -119,9 +119,9 @@ struct NdDims {
   static constexpr int Z = N * (2 * N + 1);        // number of moments, |n| <= 2N-1
   static constexpr int M = 2 * N;                  // orders 0..2N-1 per dimension
   static constexpr int SS = S * S;
-  // per-warp shared memory in doubles: ms, R, K[2], V[2], wts, lam[2], rotation (c, s) for up to 32 pairs
-  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 64;
-  static constexpr int kInts = 64;                 // rotation (p, q)
+  // per-warp shared memory in doubles: ms, R, K[2], V[2], wts, lam[2], and d / e / Householder v / w per matrix
+  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 8 * S;
+  static constexpr int kInts = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -137,7 +137,7 @@ MFS_DEV int quadrature_nd(const NdArgs& P, double* sm, int* si, int lane) {   //
   double* V = K + 2 * SS;      // V[0], V[1]
   double* wts = V + 2 * SS;
   double* lam = wts + SS;      // lam[0][S], lam[1][S]
-  double* rot = lam + 2 * S;   // c[32], s[32]
+  double* rot = lam + 2 * S;   // [8][S] scratch of the eigen-solver
 
   // gather G and both Hankel matrices
   for (int e = lane; e < SS; e += 32) {
@@ -199,80 +199,148 @@ MFS_DEV int quadrature_nd(const NdArgs& P, double* sm, int* si, int lane) {   //
   }
   __syncwarp();
 
-  // cyclic Jacobi, round-robin ordering, both matrices at once
-  constexpr int Mp = (S % 2 == 0) ? S : S + 1;   // players (with a dummy when S is odd)
-  constexpr int HP = Mp / 2;                     // pairs per round and matrix
-  bool converged = false;
-  for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
-    for (int round = 0; round < Mp - 1; ++round) {
-      if (lane < 2 * HP) {
-        const int k = lane / HP, slot = lane % HP;
-        int p = (slot == 0) ? (Mp - 1) : (round + slot) % (Mp - 1);
-        int q = (round - slot + (Mp - 1)) % (Mp - 1);
-        if (p > q) { const int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0;
-        if (q < S && p != q) {
-          const double* A = K + k * SS;
-          const double apq = A[p * S + q], app = A[p * S + p], aqq = A[q * S + q];
-          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) + 1e-20 * (fabs(app) + fabs(aqq))) {
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-            c = rsqrt(fma(t, t, 1.0));
-            s = t * c;
+  // Both K_k are diagonalised the LAPACK way (what jax.lax.linalg.eigh runs at these sizes): Householder reduction to
+  // tridiagonal form with the reflectors accumulated in V, then implicit-shift QL with the rotations applied to V.
+  // Lane r owns ROW r of its matrix (of K during the reduction, of V throughout); for S <= 16 the two matrices sit in
+  // the two half-warps and are processed at the same time, otherwise one after the other.  The scalar recurrences
+  // (reflector norms, QL rotations) are computed redundantly by every lane of a group, so there is no broadcast step.
+  constexpr int LPM = (S <= 16) ? 16 : 32;       // lanes per matrix
+  constexpr int NPASS = (S <= 16) ? 1 : 2;
+  double* dd = rot;            // [2][S] diagonal
+  double* ee = rot + 2 * S;    // [2][S] sub-diagonal, ee[i] couples i and i+1
+  double* hv = rot + 4 * S;    // [2][S] Householder vector
+  double* hw = rot + 6 * S;    // [2][S] w = p - kappa v
+  int fail = 0;
+#pragma unroll 1
+  for (int ps = 0; ps < NPASS; ++ps) {
+    const int k = (LPM == 16) ? (lane >> 4) : ps;
+    const int r = lane & (LPM - 1);
+    const bool act = r < S;
+    double* A = K + k * SS;
+    double* Q = V + k * SS;
+    double* d = dd + k * S;
+    double* e = ee + k * S;
+    double* v = hv + k * S;
+    double* w = hw + k * S;
+    auto group_sum = [&](double x) {
+#pragma unroll
+      for (int o = LPM / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      return x;
+    };
+    // ---- Householder tridiagonalisation: column j is reduced by H_j = I - tau v v^T acting on indices j+1..S-1.
+    //      Control flow is uniform over the warp (an already reduced column runs with tau = 0).
+    for (int j = 0; j + 2 < S; ++j) {
+      const double xr = (act && r > j) ? A[r * S + j] : 0.0;
+      const double sigma = group_sum(xr * xr);
+      const double x0 = A[(j + 1) * S + j];
+      const double tail = sigma - x0 * x0;
+      const bool skip = !(tail > 0.0) || !(sigma > 0.0);   // nothing below the sub-diagonal: H_j = I
+      double alpha = x0, tau = 0.0;
+      if (!skip) {
+        alpha = -copysign(sqrt(sigma), x0);
+        tau = 1.0 / (alpha * (alpha - x0));
+      }
+      const double vr = (act && r > j) ? ((r == j + 1) ? xr - alpha : xr) : 0.0;
+      if (act && r > j) v[r] = vr;
+      __syncwarp();
+      double pr = 0.0;
+      if (act && r > j) {
+        for (int c = j + 1; c < S; ++c) pr = fma(A[r * S + c], v[c], pr);
+        pr *= tau;
+      }
+      const double kappa = 0.5 * tau * group_sum(vr * pr);
+      const double wr = fma(-kappa, vr, pr);
+      if (act && r > j) w[r] = wr;
+      __syncwarp();
+      if (act && r > j) {
+        for (int c = j + 1; c < S; ++c) A[r * S + c] -= fma(vr, w[c], wr * v[c]);
+      }
+      if (act) {   // V <- V H_j
+        double sq = 0.0;
+        for (int c = j + 1; c < S; ++c) sq = fma(Q[r * S + c], v[c], sq);
+        sq *= tau;
+        for (int c = j + 1; c < S; ++c) Q[r * S + c] = fma(-sq, v[c], Q[r * S + c]);
+      }
+      if (r == j) { d[j] = A[j * S + j]; e[j] = alpha; }
+      __syncwarp();
+    }
+    if (r == 0) {
+      if (S >= 2) { d[S - 2] = A[(S - 2) * S + (S - 2)]; e[S - 2] = A[(S - 1) * S + (S - 2)]; }
+      d[S - 1] = A[(S - 1) * S + (S - 1)];
+      e[S - 1] = 0.0;
+    }
+    __syncwarp();
+    // ---- implicit-shift QL.  Every lane runs the same scalar recurrence on its PRIVATE copy of (d, e) (local memory:
+    //      dynamic indices, no cross-lane hazards, no barriers inside data-dependent loops) and rotates its own row of V.
+    double qd[S], qe[S];
+    for (int i = 0; i < S; ++i) { qd[i] = d[i]; qe[i] = e[i]; }
+    bool bad = false;
+    for (int l = 0; l < S && !bad; ++l) {
+      int iter = 0;
+      while (true) {
+        int m = l;
+        for (; m < S - 1; ++m) {
+          const double tst = fabs(qd[m]) + fabs(qd[m + 1]);
+          if (fabs(qe[m]) <= kEps * tst) break;
+        }
+        if (m == l) break;
+        if (++iter > 60) { bad = true; break; }
+        const double el = qe[l];
+        double g = (qd[l + 1] - qd[l]) / (2.0 * el);
+        double rr = sqrt(fma(g, g, 1.0));
+        g = qd[m] - qd[l] + el / (g + copysign(rr, g));
+        double sn = 1.0, cs = 1.0, pp = 0.0;
+        double d_up = qd[m];              // d[i+1] as it was before this sweep
+        double e_i = qe[m - 1], d_i = qd[m - 1];
+        bool underflow = false;
+        for (int i = m - 1; i >= l; --i) {
+          const double e_nx = (i > l) ? qe[i - 1] : 0.0, d_nx = (i > l) ? qd[i - 1] : 0.0;   // prefetch
+          const double f = sn * e_i, b = cs * e_i;
+          const double h2 = fma(f, f, g * g);
+          if (h2 == 0.0) {               // recover from underflow
+            qd[i + 1] = d_up - pp;
+            qe[m] = 0.0;
+            underflow = true;
+            break;
           }
-        } else {
-          p = q = -1;
+          const double rinv = rsqrt_fast(h2);
+          qe[i + 1] = h2 * rinv;
+          sn = f * rinv;
+          cs = g * rinv;
+          g = d_up - pp;
+          rr = fma(d_i - g, sn, 2.0 * cs * b);
+          pp = sn * rr;
+          qd[i + 1] = g + pp;
+          g = fma(cs, rr, -b);
+          if (act) {
+            const double z1 = Q[r * S + i + 1], z0 = Q[r * S + i];
+            Q[r * S + i + 1] = fma(sn, z0, cs * z1);
+            Q[r * S + i] = fma(cs, z0, -sn * z1);
+          }
+          d_up = d_i;
+          e_i = e_nx;
+          d_i = d_nx;
         }
-        rot[lane] = c;
-        rot[32 + lane] = s;
-        si[lane] = p;
-        si[32 + lane] = q;
+        if (underflow) continue;
+        qd[l] = d_up - pp;
+        qe[l] = g;
+        qe[m] = 0.0;
       }
-      __syncwarp();
-      // rows: (A[p][j], A[q][j]) <- (c A[p][j] - s A[q][j], s A[p][j] + c A[q][j])
-      for (int e = lane; e < 2 * HP * S; e += 32) {
-        const int pr = e / S, j = e % S, p = si[pr], q = si[32 + pr];
-        if (p >= 0) {
-          double* A = K + (pr / HP) * SS;
-          const double c = rot[pr], s = rot[32 + pr];
-          const double x = A[p * S + j], y = A[q * S + j];
-          A[p * S + j] = fma(c, x, -s * y);
-          A[q * S + j] = fma(s, x, c * y);
-        }
-      }
-      __syncwarp();
-      // columns of A and of V
-      for (int e = lane; e < 2 * HP * S; e += 32) {
-        const int pr = e / S, i = e % S, p = si[pr], q = si[32 + pr];
-        if (p >= 0) {
-          double* A = K + (pr / HP) * SS;
-          double* W = V + (pr / HP) * SS;
-          const double c = rot[pr], s = rot[32 + pr];
-          const double x = A[i * S + p], y = A[i * S + q];
-          A[i * S + p] = fma(c, x, -s * y);
-          A[i * S + q] = fma(s, x, c * y);
-          const double u = W[i * S + p], v = W[i * S + q];
-          W[i * S + p] = fma(c, u, -s * v);
-          W[i * S + q] = fma(s, u, c * v);
-        }
-      }
-      __syncwarp();
     }
-    // convergence: off-diagonal mass against diagonal mass, both matrices
-    double off = 0.0, dia = 0.0;
-    for (int e = lane; e < 2 * SS; e += 32) {
-      const int r = (e % SS) / S, c = e % S;
-      const double v = K[e];
-      if (r == c) dia = fma(v, v, dia); else off = fma(v, v, off);
+    if (r == 0) {
+      for (int i = 0; i < S; ++i) d[i] = qd[i];
     }
-    off = warp_sum(off);
-    dia = warp_sum(dia);
-    // rounding keeps the off-diagonal mass near (eps |K|)^2 * (#entries) ~ 1e-30 |K|^2: stop an order above that floor
-    converged = !(off > 1e-28 * dia);
-    if (!(off == off)) return 3;
+    if (bad) fail = 1;
+    __syncwarp();
   }
-  if (!converged) return 2;
-  for (int e = lane; e < 2 * S; e += 32) lam[e] = K[(e / S) * SS + (e % S) * S + (e % S)];
+  if (__any_sync(0xffffffffu, fail)) return 2;
+  {
+    double chk = 0.0;
+    for (int e = lane; e < 2 * S; e += 32) chk += dd[e];
+    chk = warp_sum(chk);
+    if (!(chk == chk)) return 3;
+  }
+  for (int e = lane; e < 2 * S; e += 32) lam[e] = dd[e];
   __syncwarp();
   // weights: <v1_i, v2_j> v1_i[0] v2_j[0]   (quadratures.py:169-170)
   for (int e = lane; e < SS; e += 32) {
