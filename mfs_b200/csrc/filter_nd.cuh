@@ -119,229 +119,262 @@ struct NdDims {
   static constexpr int Z = N * (2 * N + 1);        // number of moments, |n| <= 2N-1
   static constexpr int M = 2 * N;                  // orders 0..2N-1 per dimension
   static constexpr int SS = S * S;
-  // per-warp shared memory in doubles: ms, R, K[2], V[2], wts, lam[2], and d / e / Householder v / w per matrix
-  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 8 * S;
-  static constexpr int kInts = 0;
+  // per-warp shared memory in doubles: ms, R, T[2], V[2], wts, lam[2], Householder v[2] / w[2]
+  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 4 * S;
+  static constexpr int kTabInts = 3 * SS;          // per CTA: gather table
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Quadrature: ms (shared) -> lam[2][S], V[2][S][S] (eigenvectors in columns), wts[S][S].  Returns false on failure.
+// Quadrature: ms (shared) -> lam[2][S], V[2][S][S] (eigenvectors in columns), wts[S][S].  0 ok, 1 pivot, 2 no convergence.
+//
+// Row-per-lane formulation, matrices in REGISTERS with compile-time indices (everything is unrolled over S):
+//   A  Cholesky of G: lane r owns row r; column j of the factor travels by shuffles.  The factor goes to shared
+//      memory once (it is only ever read as a warp-wide broadcast afterwards).
+//   B  K_k = R^-1 H_k R^-T: lane c forward-substitutes column c of H_k (Y = R^-1 H_k), the columns are transposed
+//      through shared memory, and a second substitution gives column c of K_k = R^-1 Y^T (H_k is symmetric);
+//      one more transpose symmetrises (jax.lax.linalg.eigh symmetrises its input).
+//   C  Householder reduction to tridiagonal form; lane r owns row r of K_k and row r of the accumulated V.
+//   D  implicit-shift QL with splitting on the tridiagonal (d, e) -- every lane of a group runs the same scalar
+//      recurrence on a private copy and rotates its own row of V.  The sweep loop is uniform over the warp, the chase
+//      is unrolled over the index range with the rotation predicated per group, and the set of negligible couplings
+//      is a bitmask maintained as the couplings are produced: the two matrices advance in lockstep.
+//   For S <= 16 the two matrices live in the two half-warps (stages B-D run once), otherwise they are processed one
+//   after the other with all 32 lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N>
-MFS_DEV int quadrature_nd(const NdArgs& P, double* sm, int* si, int lane) {   // 0 ok, 1 pivot, 2 no convergence, 3 NaN
+MFS_DEV int quadrature_nd(double* sm, const int* __restrict__ tab, int lane) {
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
+  constexpr unsigned kFull = 0xffffffffu;
   double* ms = sm;
-  double* R = ms + D::Z;
-  double* K = R + SS;          // K[0], K[1]
-  double* V = K + 2 * SS;      // V[0], V[1]
+  double* R = ms + D::Z;       // [S][S] Cholesky factor
+  double* T = R + SS;          // [2][S][S] transpose buffers
+  double* V = T + 2 * SS;      // [2][S][S]
   double* wts = V + 2 * SS;
-  double* lam = wts + SS;      // lam[0][S], lam[1][S]
-  double* rot = lam + 2 * S;   // [8][S] scratch of the eigen-solver
+  double* lam = wts + SS;      // [2][S]
+  double* hv = lam + 2 * S;    // [2][S] Householder v
+  double* hw = hv + 2 * S;     // [2][S] Householder w
 
-  // gather G and both Hankel matrices
-  for (int e = lane; e < SS; e += 32) {
-    R[e] = ms[__ldg(P.inds + e)];
-    K[e] = ms[__ldg(P.inds + SS + e)];
-    K[SS + e] = ms[__ldg(P.inds + 2 * SS + e)];
-  }
-  __syncwarp();
-
-  // Cholesky (lower, in place, right-looking).  Failure <=> a pivot is not > 0 (jax: NaN-filled factor).
-  bool ok = true;
-  for (int j = 0; j < S; ++j) {
-    const double piv = R[j * S + j];
-    if (!(piv > 0.0)) { ok = false; break; }
-    const double rinv = rsqrt_fast(piv);
-    __syncwarp();
-    for (int i = j + lane; i < S; i += 32) R[i * S + j] = (i == j) ? piv * rinv : R[i * S + j] * rinv;
-    __syncwarp();
-    // trailing update: R[i][k] -= R[i][j] R[k][j],  j < k <= i
-    const int m = S - j - 1;
-    for (int e = lane; e < m * m; e += 32) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) R[i * S + k] = fma(-R[i * S + j], R[k * S + j], R[i * S + k]);
+  // ---- A: Cholesky (lower).  Failure <=> a pivot is not > 0 (jax: NaN-filled factor).
+  double rdi[S];               // 1 / R[j][j], identical in every lane
+  {
+    const int rr = (lane < S) ? lane : 0;
+    double g[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) g[c] = ms[tab[rr * S + c]];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const double piv = __shfl_sync(kFull, g[j], j);
+      if (!(piv > 0.0)) return 1;
+      const double rinv = rsqrt_fast(piv);
+      rdi[j] = rinv;
+      g[j] *= rinv;                                   // L[r][j] for r >= j
+#pragma unroll
+      for (int c = j + 1; c < S; ++c) {
+        const double lcj = __shfl_sync(kFull, g[j], c);
+        g[c] = fma(-g[j], lcj, g[c]);                 // only the entries c <= r are ever used
+      }
     }
-    __syncwarp();
-  }
-  if (!ok) return 1;
-
-  // K_k <- R^-1 H_k R^-T.  Step 1: columns of Y = R^-1 H (lane per (k, column)); step 2: rows of K = Y R^-T.
-  for (int task = lane; task < 2 * S; task += 32) {
-    double* A = K + (task / S) * SS;
-    const int c = task % S;
-    for (int i = 0; i < S; ++i) {
-      double acc = A[i * S + c];
-      for (int q = 0; q < i; ++q) acc = fma(-R[i * S + q], A[q * S + c], acc);
-      A[i * S + c] = acc / R[i * S + i];
+    if (lane < S) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) R[lane * S + c] = g[c];
     }
   }
   __syncwarp();
-  for (int task = lane; task < 2 * S; task += 32) {
-    double* A = K + (task / S) * SS;
-    const int r = task % S;
-    for (int i = 0; i < S; ++i) {
-      double acc = A[r * S + i];
-      for (int q = 0; q < i; ++q) acc = fma(-R[i * S + q], A[r * S + q], acc);
-      A[r * S + i] = acc / R[i * S + i];
-    }
-  }
-  __syncwarp();
-  // symmetrise (jax.lax.linalg.eigh symmetrises its input) and set V = I
-  for (int e = lane; e < 2 * SS; e += 32) {
-    const int k = e / SS, r = (e % SS) / S, c = e % S;
-    if (c < r) {
-      const double v = 0.5 * (K[k * SS + r * S + c] + K[k * SS + c * S + r]);
-      K[k * SS + r * S + c] = v;
-      K[k * SS + c * S + r] = v;
-    }
-    V[e] = (r == c) ? 1.0 : 0.0;
-  }
-  __syncwarp();
 
-  // Both K_k are diagonalised the LAPACK way (what jax.lax.linalg.eigh runs at these sizes): Householder reduction to
-  // tridiagonal form with the reflectors accumulated in V, then implicit-shift QL with the rotations applied to V.
-  // Lane r owns ROW r of its matrix (of K during the reduction, of V throughout); for S <= 16 the two matrices sit in
-  // the two half-warps and are processed at the same time, otherwise one after the other.  The scalar recurrences
-  // (reflector norms, QL rotations) are computed redundantly by every lane of a group, so there is no broadcast step.
   constexpr int LPM = (S <= 16) ? 16 : 32;       // lanes per matrix
   constexpr int NPASS = (S <= 16) ? 1 : 2;
-  double* dd = rot;            // [2][S] diagonal
-  double* ee = rot + 2 * S;    // [2][S] sub-diagonal, ee[i] couples i and i+1
-  double* hv = rot + 4 * S;    // [2][S] Householder vector
-  double* hw = rot + 6 * S;    // [2][S] w = p - kappa v
+  constexpr unsigned kBits = (1u << S) - 1u;
   int fail = 0;
 #pragma unroll 1
   for (int ps = 0; ps < NPASS; ++ps) {
     const int k = (LPM == 16) ? (lane >> 4) : ps;
     const int r = lane & (LPM - 1);
+    const int gbase = lane & ~(LPM - 1);
     const bool act = r < S;
-    double* A = K + k * SS;
-    double* Q = V + k * SS;
-    double* d = dd + k * S;
-    double* e = ee + k * S;
+    const int cc = act ? r : 0;
+    double* Tk = T + k * SS;
     double* v = hv + k * S;
     double* w = hw + k * S;
     auto group_sum = [&](double x) {
 #pragma unroll
-      for (int o = LPM / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      for (int o = LPM / 2; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
       return x;
     };
-    // ---- Householder tridiagonalisation: column j is reduced by H_j = I - tau v v^T acting on indices j+1..S-1.
-    //      Control flow is uniform over the warp (an already reduced column runs with tau = 0).
+    auto solve = [&](double (&y)[S]) {               // y <- R^-1 y  (R broadcast from shared memory)
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        double acc = y[i];
+#pragma unroll
+        for (int q = 0; q < i; ++q) acc = fma(-R[i * S + q], y[q], acc);
+        y[i] = acc * rdi[i];
+      }
+    };
+    // ---- B
+    double a[S];
+    {
+      double y[S];
+#pragma unroll
+      for (int i = 0; i < S; ++i) y[i] = ms[tab[(1 + k) * SS + i * S + cc]];      // column cc of H_k
+      solve(y);
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) Tk[i * S + r] = y[i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < S; ++i) y[i] = Tk[cc * S + i];                          // row cc of Y
+      __syncwarp();
+      solve(y);                                                                   // column cc of K_k
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) Tk[i * S + r] = y[i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < S; ++i) a[i] = 0.5 * (y[i] + Tk[cc * S + i]);           // row cc of the symmetrised K_k
+    }
+    // ---- C
+    double z[S];
+    double qd[S], qe[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) z[c] = (c == r) ? 1.0 : 0.0;
+#pragma unroll
     for (int j = 0; j + 2 < S; ++j) {
-      const double xr = (act && r > j) ? A[r * S + j] : 0.0;
+      const bool below = act && r > j;
+      const double xr = below ? a[j] : 0.0;
       const double sigma = group_sum(xr * xr);
-      const double x0 = A[(j + 1) * S + j];
+      const double x0 = __shfl_sync(kFull, a[j], gbase + j + 1);
       const double tail = sigma - x0 * x0;
       const bool skip = !(tail > 0.0) || !(sigma > 0.0);   // nothing below the sub-diagonal: H_j = I
       double alpha = x0, tau = 0.0;
       if (!skip) {
         alpha = -copysign(sqrt(sigma), x0);
-        tau = 1.0 / (alpha * (alpha - x0));
+        tau = rcp_fast(alpha * (alpha - x0));
       }
-      const double vr = (act && r > j) ? ((r == j + 1) ? xr - alpha : xr) : 0.0;
-      if (act && r > j) v[r] = vr;
+      const double vr = below ? ((r == j + 1) ? xr - alpha : xr) : 0.0;
+      if (act) v[r] = vr;
       __syncwarp();
-      double pr = 0.0;
-      if (act && r > j) {
-        for (int c = j + 1; c < S; ++c) pr = fma(A[r * S + c], v[c], pr);
-        pr *= tau;
+      double vc[S];
+      double pr = 0.0, sq = 0.0;
+#pragma unroll
+      for (int c = j + 1; c < S; ++c) {
+        vc[c] = v[c];
+        pr = fma(a[c], vc[c], pr);
+        sq = fma(z[c], vc[c], sq);
       }
+      pr = below ? pr * tau : 0.0;
+      sq *= tau;
       const double kappa = 0.5 * tau * group_sum(vr * pr);
       const double wr = fma(-kappa, vr, pr);
-      if (act && r > j) w[r] = wr;
+      if (act) w[r] = wr;
       __syncwarp();
-      if (act && r > j) {
-        for (int c = j + 1; c < S; ++c) A[r * S + c] -= fma(vr, w[c], wr * v[c]);
+#pragma unroll
+      for (int c = j + 1; c < S; ++c) {
+        a[c] -= fma(vr, w[c], wr * vc[c]);            // rows r <= j have vr = wr = 0
+        z[c] = fma(-sq, vc[c], z[c]);                 // V <- V H_j
       }
-      if (act) {   // V <- V H_j
-        double sq = 0.0;
-        for (int c = j + 1; c < S; ++c) sq = fma(Q[r * S + c], v[c], sq);
-        sq *= tau;
-        for (int c = j + 1; c < S; ++c) Q[r * S + c] = fma(-sq, v[c], Q[r * S + c]);
-      }
-      if (r == j) { d[j] = A[j * S + j]; e[j] = alpha; }
-      __syncwarp();
+      qd[j] = __shfl_sync(kFull, a[j], gbase + j);
+      qe[j] = alpha;
     }
-    if (r == 0) {
-      if (S >= 2) { d[S - 2] = A[(S - 2) * S + (S - 2)]; e[S - 2] = A[(S - 1) * S + (S - 2)]; }
-      d[S - 1] = A[(S - 1) * S + (S - 1)];
-      e[S - 1] = 0.0;
+    if (S >= 2) {
+      qd[S - 2] = __shfl_sync(kFull, a[S - 2], gbase + S - 2);
+      qe[S - 2] = __shfl_sync(kFull, a[S - 2], gbase + S - 1);
     }
-    __syncwarp();
-    // ---- implicit-shift QL.  Every lane runs the same scalar recurrence on its PRIVATE copy of (d, e) (local memory:
-    //      dynamic indices, no cross-lane hazards, no barriers inside data-dependent loops) and rotates its own row of V.
-    double qd[S], qe[S];
-    for (int i = 0; i < S; ++i) { qd[i] = d[i]; qe[i] = e[i]; }
-    bool bad = false;
-    for (int l = 0; l < S && !bad; ++l) {
-      int iter = 0;
-      while (true) {
-        int m = l;
-        for (; m < S - 1; ++m) {
-          const double tst = fabs(qd[m]) + fabs(qd[m + 1]);
-          if (fabs(qe[m]) <= kEps * tst) break;
+    qd[S - 1] = __shfl_sync(kFull, a[S - 1], gbase + S - 1);
+    qe[S - 1] = 0.0;
+    // ---- D
+    unsigned neg = 1u << (S - 1);            // bit i <=> coupling e[i] negligible; bit S-1 is a sentinel
+#pragma unroll
+    for (int i = 0; i + 1 < S; ++i)
+      if (fabs(qe[i]) <= kEps * (fabs(qd[i]) + fabs(qd[i + 1]))) neg |= 1u << i;
+    int l = 0, iter = 0;
+    bool done = false, bad = false;
+    for (;;) {
+      int m = 0;
+      if (!done) {
+        const unsigned active = ~neg & kBits & (~0u << l);
+        if (active == 0u) {
+          done = true;
+        } else {
+          const int l_new = __ffs(active) - 1;      // first unreduced block starts here ...
+          if (l_new != l) { l = l_new; iter = 0; }
+          m = __ffs(neg & (~0u << l)) - 1;          // ... and ends at m > l
+          if (++iter > 40) { bad = true; done = true; }
         }
-        if (m == l) break;
-        if (++iter > 60) { bad = true; break; }
-        const double el = qe[l];
-        double g = (qd[l + 1] - qd[l]) / (2.0 * el);
-        double rr = sqrt(fma(g, g, 1.0));
-        g = qd[m] - qd[l] + el / (g + copysign(rr, g));
-        double sn = 1.0, cs = 1.0, pp = 0.0;
-        double d_up = qd[m];              // d[i+1] as it was before this sweep
-        double e_i = qe[m - 1], d_i = qd[m - 1];
-        bool underflow = false;
-        for (int i = m - 1; i >= l; --i) {
-          const double e_nx = (i > l) ? qe[i - 1] : 0.0, d_nx = (i > l) ? qd[i - 1] : 0.0;   // prefetch
+      }
+      if (__all_sync(kFull, done)) break;
+      int hi = done ? 0 : m, lo = done ? S : l;
+      if (LPM == 16) {
+        hi = max(hi, __shfl_xor_sync(kFull, hi, 16));
+        lo = min(lo, __shfl_xor_sync(kFull, lo, 16));
+      }
+      double g = 0.0, sn = 1.0, cs = 1.0, pp = 0.0;
+      if (!done) {   // Wilkinson shift (dynamic reads: qd / qe live in local memory)
+        const double el = qe[l], dl = qd[l];
+        const double ah = (qd[l + 1] - dl) * rcp_fast(2.0 * el);
+        g = qd[m] - dl + el * rcp_fast(ah + copysign(sqrt_fast(fma(ah, ah, 1.0)), ah));
+      }
+      bool stop = done;
+      double d_below = 0.0;                  // d[i+2] as left by the previous rotation
+#pragma unroll
+      for (int i = S - 2; i >= 0; --i) {
+        if (i < lo) break;
+        if (i < hi && !stop && i < m && i >= l) {
+          const double e_i = qe[i], d_i = qd[i], d_up = qd[i + 1];
           const double f = sn * e_i, b = cs * e_i;
           const double h2 = fma(f, f, g * g);
-          if (h2 == 0.0) {               // recover from underflow
+          if (h2 == 0.0) {                   // underflow: the matrix splits here
             qd[i + 1] = d_up - pp;
-            qe[m] = 0.0;
-            underflow = true;
-            break;
+            qe[i + 1] = 0.0;
+            neg |= 1u << (i + 1);
+            stop = true;
+          } else {
+            const double rinv = rsqrt_fast(h2);
+            const double e_new = h2 * rinv;
+            qe[i + 1] = e_new;
+            sn = f * rinv;
+            cs = g * rinv;
+            g = d_up - pp;
+            const double rr = fma(d_i - g, sn, (cs + cs) * b);
+            pp = sn * rr;
+            const double d_new = g + pp;
+            qd[i + 1] = d_new;
+            g = fma(cs, rr, -b);
+            const double z1 = z[i + 1];
+            z[i + 1] = fma(sn, z[i], cs * z1);
+            z[i] = fma(cs, z[i], -sn * z1);
+            // e[i+1] and d[i+1], d[i+2] are final for this sweep: refresh the negligibility bit
+            const bool small = e_new <= kEps * (fabs(d_new) + fabs(d_below));
+            neg = small ? (neg | (1u << (i + 1))) : (neg & ~(1u << (i + 1)));
+            d_below = d_new;
           }
-          const double rinv = rsqrt_fast(h2);
-          qe[i + 1] = h2 * rinv;
-          sn = f * rinv;
-          cs = g * rinv;
-          g = d_up - pp;
-          rr = fma(d_i - g, sn, 2.0 * cs * b);
-          pp = sn * rr;
-          qd[i + 1] = g + pp;
-          g = fma(cs, rr, -b);
-          if (act) {
-            const double z1 = Q[r * S + i + 1], z0 = Q[r * S + i];
-            Q[r * S + i + 1] = fma(sn, z0, cs * z1);
-            Q[r * S + i] = fma(cs, z0, -sn * z1);
-          }
-          d_up = d_i;
-          e_i = e_nx;
-          d_i = d_nx;
         }
-        if (underflow) continue;
-        qd[l] = d_up - pp;
-        qe[l] = g;
+      }
+      if (!done) {
         qe[m] = 0.0;
+        neg |= 1u << m;
+        if (!stop) {
+          const double dl = qd[l] - pp;
+          qd[l] = dl;
+          qe[l] = g;
+          const bool small = fabs(g) <= kEps * (fabs(dl) + fabs(qd[l + 1]));
+          neg = small ? (neg | (1u << l)) : (neg & ~(1u << l));
+        }
       }
     }
-    if (r == 0) {
-      for (int i = 0; i < S; ++i) d[i] = qd[i];
-    }
     if (bad) fail = 1;
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) V[k * SS + r * S + c] = z[c];
+    }
+    if (r == 0) {
+#pragma unroll
+      for (int i = 0; i < S; ++i) lam[k * S + i] = qd[i];
+    }
     __syncwarp();
   }
-  if (__any_sync(0xffffffffu, fail)) return 2;
-  {
-    double chk = 0.0;
-    for (int e = lane; e < 2 * S; e += 32) chk += dd[e];
-    chk = warp_sum(chk);
-    if (!(chk == chk)) return 3;
-  }
-  for (int e = lane; e < 2 * S; e += 32) lam[e] = dd[e];
-  __syncwarp();
+  if (__any_sync(kFull, fail)) return 2;
   // weights: <v1_i, v2_j> v1_i[0] v2_j[0]   (quadratures.py:169-170)
   for (int e = lane; e < SS; e += 32) {
     const int i = e / S, j = e % S;
@@ -422,16 +455,22 @@ MFS_DEV void accumulate_tme_moments(double wgt, double dl1, double dl2, const do
   }
 }
 
+#ifndef MFS_ND_MIN_BLOCKS
+#define MFS_ND_MIN_BLOCKS 2
+#endif
 template <int N>
-__global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P) {
+__global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_kernel(const NdArgs P) {
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS, Z = D::Z, M = D::M;
   extern __shared__ double smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * kNdWarps + warp;
+  // the (3, S, S) gather table, shared by the CTA's warps
+  int* tab = reinterpret_cast<int*>(smem_all + kNdWarps * D::kDoubles);
+  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = __ldg(P.inds + e);
+  __syncthreads();
   if (b >= P.B) return;
-  double* sm = smem_all + warp * (D::kDoubles + D::kInts / 2);
-  int* si = reinterpret_cast<int*>(sm + D::kDoubles);
+  double* sm = smem_all + warp * D::kDoubles;
   double* ms = sm;
   double* wts = sm + Z + 5 * SS;
   double* lam = wts + SS;
@@ -458,7 +497,7 @@ __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P
   for (; t < P.T; ++t) {
     const double y = (double)__ldg(P.ys + b * P.T + t);
     // ---------------- prediction ----------------
-    int why = quadrature_nd<N>(P, sm, si, lane);
+    int why = quadrature_nd<N>(sm, tab, lane);
     if (why) { status = (int)t; reason = why; break; }
     double acc[Z];
     const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
@@ -514,7 +553,7 @@ __global__ void __launch_bounds__(kNdWarps * 32) filter_nd_kernel(const NdArgs P
     }
     __syncwarp();
     // ---------------- update ----------------
-    why = quadrature_nd<N>(P, sm, si, lane);
+    why = quadrature_nd<N>(sm, tab, lane);
     if (why) { status = (int)t; reason = why + 4; break; }
     MeasStep st;
     st.y = y;

@@ -6,7 +6,7 @@ namespace mfs {
 template <int N>
 cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream) {
   using D = NdDims<N>;
-  const size_t smem = sizeof(double) * kNdWarps * (D::kDoubles + D::kInts / 2);
+  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
   static bool configured = false;   // benign race: the attribute is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(filter_nd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
