@@ -142,7 +142,7 @@ struct NdDims {
 //   after the other with all 32 lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N>
-MFS_DEV int quadrature_nd(double* sm, const int* __restrict__ tab, int lane) {
+__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane) {   // one copy, two call sites
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
   constexpr unsigned kFull = 0xffffffffu;
@@ -455,6 +455,30 @@ MFS_DEV void accumulate_tme_moments(double wgt, double dl1, double dl2, const do
   }
 }
 
+// ms[p] = scale * (sum over the warp's lanes of acc[p]) for all Z moments, through a shared-memory scratch of 4 S^2
+// doubles (the transpose / eigenvector buffers, idle outside the quadrature): each lane drops its partial sums in a
+// skewed [moment][lane] tile (conflict-free in both directions) and lane q adds up moment q.  One rolled summation loop
+// instead of Z unrolled butterfly reductions (the latter were 60 % of the kernel's code size).
+template <int N>
+MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scratch, double* ms, double scale, int lane) {
+  constexpr int Z = NdDims<N>::Z, SS = NdDims<N>::SS;
+  constexpr int BS = (4 * SS / 32 > 32) ? 32 : (4 * SS / 32 < 1 ? 1 : 4 * SS / 32);   // moments per batch
+#pragma unroll
+  for (int p0 = 0; p0 < Z; p0 += BS) {
+#pragma unroll
+    for (int q = 0; q < BS; ++q)
+      if (p0 + q < Z) scratch[q * 32 + ((lane + q) & 31)] = acc[p0 + q];
+    __syncwarp();
+    if (lane < BS && p0 + lane < Z) {
+      double sum = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) sum += scratch[lane * 32 + ((j + lane) & 31)];
+      ms[p0 + lane] = sum * scale;
+    }
+    __syncwarp();
+  }
+}
+
 #ifndef MFS_ND_MIN_BLOCKS
 #define MFS_ND_MIN_BLOCKS 2
 #endif
@@ -472,6 +496,7 @@ __global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_ke
   if (b >= P.B) return;
   double* sm = smem_all + warp * D::kDoubles;
   double* ms = sm;
+  double* scratch = sm + Z + SS;      // T and V of the quadrature (4 S^2 doubles), idle between quadratures
   double* wts = sm + Z + 5 * SS;
   double* lam = wts + SS;
 
@@ -501,7 +526,9 @@ __global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_ke
     if (why) { status = (int)t; reason = why; break; }
     double acc[Z];
     const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
-    if (P.mode == MFS_MODE_CENTRAL) {
+    const bool central = P.mode == MFS_MODE_CENTRAL;
+    double nm1 = 0.0, nm2 = 0.0;       // centre of the predicted moments (0 in raw mode, where mean1 = mean2 = 0 too)
+    if (central) {
       double s1 = 0.0, s2 = 0.0;
       for (int e = lane; e < SS; e += 32) {
         const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
@@ -511,47 +538,26 @@ __global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_ke
         s1 = fma(wts[e], m1, s1);
         s2 = fma(wts[e], m2, s2);
       }
-      const double nm1 = warp_sum(s1), nm2 = warp_sum(s2);
-      // nodes still refer to the old mean; keep both
+      nm1 = warp_sum(s1);
+      nm2 = warp_sum(s2);
+    }
 #pragma unroll
-      for (int p = 0; p < Z; ++p) acc[p] = 0.0;
-      for (int e = lane; e < SS; e += 32) {
-        const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
-        if (tme_full) {
-          double G[5][5];
-          lv_tme_operator(P.tme_order, x1, x2, P.dt, tp, G);
-          accumulate_tme_moments<N>(wts[e], x1 - nm1, x2 - nm2, G, acc);
-        } else {
-          double m1, m2, c11, c12, c22;
-          lv_mean_cov(P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
-          accumulate_gaussian_moments<N>(wts[e], m1 - nm1, m2 - nm2, c11, c12, c22, acc);
-        }
-      }
-      mean1 = nm1;
-      mean2 = nm2;
-    } else {
-#pragma unroll
-      for (int p = 0; p < Z; ++p) acc[p] = 0.0;
-      for (int e = lane; e < SS; e += 32) {
-        const double x1 = lam[e / S], x2 = lam[S + e % S];
-        if (tme_full) {
-          double G[5][5];
-          lv_tme_operator(P.tme_order, x1, x2, P.dt, tp, G);
-          accumulate_tme_moments<N>(wts[e], x1, x2, G, acc);
-        } else {
-          double m1, m2, c11, c12, c22;
-          lv_mean_cov(P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
-          accumulate_gaussian_moments<N>(wts[e], m1, m2, c11, c12, c22, acc);
-        }
+    for (int p = 0; p < Z; ++p) acc[p] = 0.0;
+    for (int e = lane; e < SS; e += 32) {      // nodes still refer to the old mean
+      const double x1 = lam[e / S] + mean1, x2 = lam[S + e % S] + mean2;
+      if (tme_full) {
+        double G[5][5];
+        lv_tme_operator(P.tme_order, x1, x2, P.dt, tp, G);
+        accumulate_tme_moments<N>(wts[e], x1 - nm1, x2 - nm2, G, acc);
+      } else {
+        double m1, m2, c11, c12, c22;
+        lv_mean_cov(P.trans_id, P.tme_order, x1, x2, P.dt, tp, m1, m2, c11, c12, c22);
+        accumulate_gaussian_moments<N>(wts[e], m1 - nm1, m2 - nm2, c11, c12, c22, acc);
       }
     }
+    if (central) { mean1 = nm1; mean2 = nm2; }
     __syncwarp();
-#pragma unroll
-    for (int p = 0; p < Z; ++p) {
-      const double v = warp_sum(acc[p]);
-      if (lane == 0) ms[p] = v;
-    }
-    __syncwarp();
+    warp_reduce_moments<N>(acc, scratch, ms, 1.0, lane);
     // ---------------- update ----------------
     why = quadrature_nd<N>(sm, tab, lane);
     if (why) { status = (int)t; reason = why + 4; break; }
@@ -592,11 +598,7 @@ __global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_ke
       }
     }
     __syncwarp();
-#pragma unroll
-    for (int p = 0; p < Z; ++p) {
-      const double v = warp_sum(acc[p]) * cinv;
-      if (lane == 0) ms[p] = v;
-    }
+    warp_reduce_moments<N>(acc, scratch, ms, cinv, lane);
     if (P.mode == MFS_MODE_CENTRAL) { mean1 = c1; mean2 = c2; }
     nell -= log(cc);
     __syncwarp();
