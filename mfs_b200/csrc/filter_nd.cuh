@@ -479,11 +479,15 @@ MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scra
   }
 }
 
-#ifndef MFS_ND_MIN_BLOCKS
-#define MFS_ND_MIN_BLOCKS 2
+// CTAs per SM the register allocation must allow (measured on B200, profiles/r1_nd_occupancy.md): the eigen-solver is a
+// latency-bound scalar recurrence, so resident warps pay until the moment accumulators start to spill.
+#ifdef MFS_ND_MIN_BLOCKS
+template <int N> constexpr int nd_min_blocks() { return MFS_ND_MIN_BLOCKS; }
+#else
+template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N == 5 ? 3 : 2; }
 #endif
 template <int N>
-__global__ void __launch_bounds__(kNdWarps * 32, MFS_ND_MIN_BLOCKS) filter_nd_kernel(const NdArgs P) {
+__global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS, Z = D::Z, M = D::M;
   extern __shared__ double smem_all[];
