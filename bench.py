@@ -121,6 +121,76 @@ def cpu_baseline(N, T, target_seconds=15., threads=0, seed=666 + 1):
     return b * T / el, int(out['threads']), f'{b} filters x T={T} (first {b} of the seeded workload), full history, {el:.1f} s', b
 
 
+def secondary_legs(device_index, fp64_peak):
+    """The other two kernels of the path, timed on the device (CUDA events, second of two runs), N=1 only:
+    the 2-D prey--predator moment filter (BASELINE configs[4] shape: N=5, central moments, TME-normal order 2) and one
+    time step of the brute-force grid filter at the paper's grid (n=2000, 100 sub-steps = 100 FP64 tensor-core GEMMs)."""
+    import math
+    import torch
+    from mfs_b200 import _lib
+    from mfs_b200.multi_dims.multi_indices import (generate_graded_lexico_multi_indices,
+                                                   gram_and_hankel_indices_graded_lexico)
+    from mfs_b200.multi_dims.filtering import moment_filter_nd_cms
+    from mfs_b200.multi_dims.moments import sde_cond_moments_tme_normal
+    from mfs_b200.multi_dims.ss_models import prey_predator
+    from mfs_b200.classical_filters_smoothers import brute_force_filter
+    from mfs_b200.functors import benes_drift, Dispersion, bernoulli_logistic_cubic
+    out = {}
+    dev = torch.device('cuda', device_index)
+
+    def timed(fn):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), r
+
+    # ---- 2-D filter
+    N, B, T = 5, 148 * 128, 50
+    mis = generate_graded_lexico_multi_indices(2, 2 * N - 1, 0)
+    inds = gram_and_hankel_indices_graded_lexico(N, 2)
+    dt, _, _, gs, drift, dispersion, _, pmf, simulate = prey_predator(mis)
+    rng = np.random.Generator(np.random.PCG64(677))
+    _, _, ys = simulate(rng, integration_steps=10, T=T, n=64)
+    ys = torch.from_numpy(np.tile(ys, (B // 64, 1)).copy()).to(dev)
+    fam = sde_cond_moments_tme_normal(drift, dispersion, dt, 2, mis)
+    ms, res = timed(lambda: moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, ys, (mis, inds), gs.cms, gs.mean,
+                                                  history='last', return_status=True))
+    s, z = N * (N + 1) // 2, N * (2 * N + 1)
+    # SURVEY.md 8(d) nominal work model of one 2-D filter step (d = 2): two quadratures + transition + update
+    w_quad = s ** 3 / 3 + 2 * 2 * s ** 3 + 9 * 2 * s ** 3 + s ** 2 * (2 * s + 2)
+    w_nd = 2 * w_quad + s ** 2 * (80 + 6 * z) + s ** 2 * (45 + 4 * z)
+    rate = B * T / (ms * 1e-3)
+    out['nd_filter'] = {'metric': 'prey_predator_2d_filter_steps_per_s', 'value': rate, 'unit': UNIT,
+                        'config': f'N={N} (z={z} moments, {s * s} nodes), central, TME-normal order 2, {B} filters x T={T}, '
+                                  f'history=last', 'kernel_ms': ms, 'nominal_flop_per_step': w_nd,
+                        'fp64_frac_nominal': rate * w_nd / fp64_peak,
+                        'diverged_frac': float((res[-1] >= 0).double().mean().item())}
+    # ---- grid filter
+    n, Bg, steps, Tg = 2000, 16384, 100, 1
+    xs = np.linspace(-6., 6., n)
+    ip = 0.5 * np.exp(-0.5 * (xs + 0.5) ** 2 / 0.05) / math.sqrt(2 * math.pi * 0.05) \
+        + 0.5 * np.exp(-0.5 * (xs - 0.5) ** 2 / 0.05) / math.sqrt(2 * math.pi * 0.05)
+    ysg = torch.from_numpy((rng.random((Bg, Tg)) < 0.5).astype(np.uint8)).to(dev)
+    ms, pdf = timed(lambda: brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip, xs,
+                                               ysg, 1e-2, integration_steps=steps, pred_method='chapman-tme-3',
+                                               history='last'))
+    dmma, _ = _lib.dmma_peak(device_index, 4096)
+    flop = 2. * n * n * Bg * steps * Tg
+    out['grid_filter'] = {'metric': 'brute_force_filter_time_steps_per_s', 'value': Bg * Tg / (ms * 1e-3),
+                          'unit': 'filter time-steps/s (each = 100 sub-step GEMMs on a 2000-point grid)',
+                          'config': f'n_grid={n}, {steps} integration sub-steps, chapman-tme-3, {Bg} records on one grid',
+                          'ms': ms, 'tflops': flop / (ms * 1e-3) / 1e12,
+                          'roofline': {'bound': 'fp64_tensor', 'achieved': flop / (ms * 1e-3) / 1e12,
+                                       'peak': dmma / 1e12, 'unit': 'TFLOP/s', 'frac': flop / (ms * 1e-3) / dmma,
+                                       'peak_source': 'measured live: mfs_dmma_peak (DMMA m8n8k4 micro-benchmark)'},
+                          'mass_check': float(torch.trapezoid(pdf[0], torch.from_numpy(xs).to(dev)))}
+    return out
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The JAX reference cannot be installed or run
     in this image (jax, jaxlib, tme absent; no network), so this arm times the C restatement of its algorithm
@@ -182,6 +252,7 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=131072, help='filters per GPU in the host-buffer (e2e) leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the 2-D filter and grid-filter legs')
     ap.add_argument('--ref-step-seconds', type=float, default=10.)
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -366,7 +437,9 @@ def main():
         peaks, peaks_src = measured_peaks()
         W = work_per_step(N, two_quadratures=False)
         W_lit = work_per_step(N, two_quadratures=True)
-        achieved_tf = W * steps_per_launch / (kernel_ms_avg * 1e-3) / 1e12
+        # flops actually executed: a filter that lost positive definiteness idles from its failing step on (NaN
+        # outputs, like the JAX scan), so only LIVE filter-steps are claimed as work
+        achieved_tf = W * steps_per_launch * live / (kernel_ms_avg * 1e-3) / 1e12
         alg_bytes = (1 + (8 * M if args.history == 'full' else 0)) * steps_per_launch
         traffic = None
         try:
@@ -389,19 +462,23 @@ def main():
                          'frac': achieved_tf / (fp64_peak / 1e12), 'traffic': traffic,
                          'peak_source': 'measured live: mfs_fp64_peak DFMA micro-benchmark on this GPU '
                                         '(MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)',
-                         'flop_per_filter_step': W, 'kernel_ms': kernel_ms_avg,
+                         'flop_per_filter_step': W, 'kernel_ms': kernel_ms_avg, 'live_step_frac': live,
+                         'achieved_counting_all_steps': W * steps_per_launch / (kernel_ms_avg * 1e-3) / 1e12,
                          'hbm': {'achieved': alg_bytes / (kernel_ms_avg * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
                                  'unit': 'GB/s', 'peak_source': peaks_src,
                                  'frac': alg_bytes / (kernel_ms_avg * 1e-3) / 1e9 / peaks['hbm_gbs'],
                                  'algorithmic_bytes_per_launch': alg_bytes}},
             'clocks': clocks, 'gpu_launches': launches_all, 'e2e': e2e, 'e2e_nell_only': e2e_nell,
-            'diverged_frac': diverged, 'live_step_frac': live, 'wall_s_timed_region': t_wall,
+            'diverged_frac': diverged, 'live_step_frac': live, 'value_live_steps_only': value * live,
+            'wall_s_timed_region': t_wall,
             'literal_two_quadratures': {
                 'value': value_literal, 'unit': UNIT, 'kernel_ms': kernel_ms_lit, 'flop_per_filter_step': W_lit,
-                'roofline_frac': W_lit * steps_per_launch / (kernel_ms_lit * 1e-3) / fp64_peak,
+                'roofline_frac': W_lit * steps_per_launch * live / (kernel_ms_lit * 1e-3) / fp64_peak,
                 'note': 'MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE: second moment_quadrature per step, as filtering.py:78'},
             'reference_horizon_T100': {'value': value_t100, 'unit': UNIT, 'T': T100, 'diverged_frac': div100},
         }
+        if world == 1 and not args.no_secondary:
+            line['secondary'] = secondary_legs(local_rank, fp64_peak)
         if world == 1 and not args.no_cpu:
             v, cores, sample, _ = cpu_baseline(N, T)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
