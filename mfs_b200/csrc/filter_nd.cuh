@@ -81,7 +81,7 @@ MFS_DEV void lv_mean_cov(int trans_id, int order, double x1, double x2, double d
 //     sum_{r <= order} dt^r / r! A^r phi = sum_{p+q <= 2 order} G[p][q](x) d1^p d2^q phi .
 // A = sum over the four "operator atoms" (i, j, c): (1,0,a1) (0,1,a2) (2,0,Gamma11/2) (0,2,Gamma22/2), and the product
 // rule of a second-order operator, A(c D) = c A D + (A c) D + Gamma11 d1c d1 D + Gamma22 d2c d2 D, gives A^2.
-// Orders 1 and 2.  tools/derive_lv_tme.py prints the same G symbolically; the oracle applies A to every monomial.
+// Orders 1 and 2.  tools/derive_lv_tme.py prints the same G symbolically; the CPU checker applies A to every monomial.
 MFS_DEV void lv_tme_operator(int order, double x1, double x2, double dt, const double* p, double (&G)[5][5]) {
   const double al = p[0], be = p[1], de = p[2], ga = p[3], sg2 = p[4] * p[4];
 #pragma unroll
