@@ -274,6 +274,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # rank 0 must print exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():

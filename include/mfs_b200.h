@@ -230,6 +230,13 @@ int mfs_release_cached_memory(void);
 int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
                              int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream);
 
+/* Characteristic function by moments (mfs/one_dim/moments.py:309-337), the post-processing step after the filter
+ * (dardel/benes_bernoulli/post_processing_mf.py:37-60): out[b][j] = sum_n w_n exp(i zs[j] x_n) with (w, x) the
+ * quadrature of ms[b][0..2N) (mean/scale may be NULL = 0 / 1).  out is complex128 [B][m] as (re, im) pairs.
+ * Device pointers.  A failed quadrature gives NaN, like the reference. */
+int mfs_characteristic_fn_1d(int32_t N, int64_t B, int64_t m, const double* ms, const double* mean, const double* scale,
+                             const double* zs, double* out, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process since load (all threads). */
 int64_t mfs_launch_count(void);
 

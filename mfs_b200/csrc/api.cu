@@ -175,6 +175,53 @@ static cudaError_t launch_quadrature(int64_t B, const double* ms, const double* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// characteristic function by moments (mfs/one_dim/moments.py:309-337): E[exp(i z X)] ~ sum_n w_n exp(i z x_n), the
+// post-processing step vmapped over (time steps x z-grid x Monte-Carlo runs) in
+// dardel/benes_bernoulli/post_processing_mf.py:37-60.  One CTA per moment vector: one thread derives the quadrature
+// (same device code as the filter), all threads sweep the z-grid.  out[b][j] = (re, im) as two doubles (complex128).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(kBlock) characteristic_kernel(int64_t m, const double* __restrict__ ms,
+                                                                const double* __restrict__ mean,
+                                                                const double* __restrict__ scale,
+                                                                const double* __restrict__ zs, double* __restrict__ out) {
+  __shared__ double sw[N], sx[N];
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double mm[2 * N], w[N], x[N];
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) mm[p] = ms[b * 2 * N + p];
+    const bool ok = moment_quadrature<N>(mm, mean ? mean[b] : 0.0, scale ? scale[b] : 1.0, w, x);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { sw[i] = ok ? w[i] : nan(""); sx[i] = ok ? x[i] : nan(""); }
+  }
+  __syncthreads();
+  double w[N], x[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { w[i] = sw[i]; x[i] = sx[i]; }
+  double2* o = reinterpret_cast<double2*>(out) + b * m;
+  for (int64_t j = threadIdx.x; j < m; j += kBlock) {
+    const double z = zs[j];
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double sn, cs;
+      sincos(z * x[i], &sn, &cs);
+      re = fma(w[i], cs, re);
+      im = fma(w[i], sn, im);
+    }
+    o[j] = make_double2(re, im);
+  }
+}
+
+template <int N>
+static cudaError_t launch_characteristic(int64_t B, int64_t m, const double* ms, const double* mean, const double* scale,
+                                         const double* zs, double* out, cudaStream_t s) {
+  characteristic_kernel<N><<<(unsigned)B, kBlock, 0, s>>>(m, ms, mean, scale, zs, out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // FP64 FMA peak micro-benchmark: 8 independent accumulator chains per thread, no memory traffic.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {
@@ -357,6 +404,27 @@ int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const doubl
 #undef MFS_CASE
   }
   if (e != cudaSuccess) return fail("quadrature launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_characteristic_fn_1d(int32_t N, int64_t B, int64_t m, const double* ms, const double* mean, const double* scale,
+                             const double* zs, double* out, void* stream) {
+  if (N < 1 || N > MFS_MAX_N) return fail("N=%d outside [1, %d]", N, MFS_MAX_N);
+  if (B < 0 || m < 0) return fail("negative B or m");
+  if (B == 0 || m == 0) return 0;
+  if (B > 0x7fffffffLL) return fail("B too large for one launch");
+  if (!ms || !zs || !out) return fail("NULL pointer");
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail("out must be 16-byte aligned (complex128)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (N) {
+#define MFS_CASE(n) case n: e = launch_characteristic<n>(B, m, ms, mean, scale, zs, out, s); break;
+    MFS_CASE(1) MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
+    MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
+#undef MFS_CASE
+  }
+  if (e != cudaSuccess) return fail("characteristic_fn launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

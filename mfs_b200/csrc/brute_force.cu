@@ -126,6 +126,86 @@ bf_gemm_kernel(const double* __restrict__ A, const double* __restrict__ Pw, doub
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Small batches (the reference's own call shape is ONE record per grid, dardel/benes_bernoulli/brute_force.py:51-55):
+// the contraction degenerates to a matrix-vector product that a 128 x 128 tile cannot fill the machine with.  Here
+// every warp owns output rows i, streams row i of Pw (L2-resident) with 16-byte loads and dots it with up to BT
+// densities held in shared memory; deterministic lane-strided partial sums + butterfly reduction.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BF_GEMV_THREADS = 256;
+constexpr int BF_GEMV_MAX_B = 64;     // batches up to this size take the matrix-vector path (in chunks of <= 8)
+
+template <int BT>
+__global__ void __launch_bounds__(BF_GEMV_THREADS)
+bf_gemv_kernel(const double* __restrict__ A, const double* __restrict__ Pw, double* __restrict__ D, int64_t M, int n,
+               int Kpad, int64_t b0) {
+  extern __shared__ __align__(16) double gv_smem[];   // [BT][Kpad]
+  for (int e = threadIdx.x * 2; e < BT * Kpad; e += BF_GEMV_THREADS * 2) {
+    const int b = e / Kpad, j = e - b * Kpad;
+    const bool ok = b0 + b < M;
+    const double2 v = ok ? *reinterpret_cast<const double2*>(A + (b0 + b) * Kpad + j) : make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(gv_smem + e) = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = BF_GEMV_THREADS / 32;
+  for (int i = blockIdx.x * kWarps + warp; i < n; i += gridDim.x * kWarps) {
+    const double* prow = Pw + (int64_t)i * Kpad;
+    double acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+    for (int j = lane * 2; j < Kpad; j += 64) {
+      const double2 p = *reinterpret_cast<const double2*>(prow + j);
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const double2 a = *reinterpret_cast<const double2*>(gv_smem + b * Kpad + j);
+        acc[b] = fma(p.y, a.y, fma(p.x, a.x, acc[b]));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      double v = acc[b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && b0 + b < M) D[(b0 + b) * Kpad + i] = v;
+    }
+  }
+}
+
+template <int BT>
+static cudaError_t launch_gemv(const double* A, const double* Pw, double* D, int64_t M, int n, int Kpad, int64_t b0,
+                               int sms, cudaStream_t s) {
+  const size_t smem = sizeof(double) * BT * Kpad;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(bf_gemv_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int rows_per_cta = BF_GEMV_THREADS / 32;
+  int grid = (n + rows_per_cta - 1) / rows_per_cta;
+  const int cap = sms * (smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4);
+  if (grid > cap) grid = cap;
+  bf_gemv_kernel<BT><<<grid, BF_GEMV_THREADS, smem, s>>>(A, Pw, D, M, n, Kpad, b0);
+  return cudaGetLastError();
+}
+
+// one integration sub-step for a small batch: chunks of up to 8 densities
+static cudaError_t gemv_substep(const double* A, const double* Pw, double* D, int64_t M, int n, int Kpad, int sms,
+                                cudaStream_t s, int64_t* launches) {
+  for (int64_t b0 = 0; b0 < M; b0 += 8) {
+    const int64_t left = M - b0;
+    cudaError_t e;
+    if (left >= 5) e = launch_gemv<8>(A, Pw, D, M, n, Kpad, b0, sms, s);
+    else if (left >= 3) e = launch_gemv<4>(A, Pw, D, M, n, Kpad, b0, sms, s);
+    else if (left == 2) e = launch_gemv<2>(A, Pw, D, M, n, Kpad, b0, sms, s);
+    else e = launch_gemv<1>(A, Pw, D, M, n, Kpad, b0, sms, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Transition operator: per column j (m_j, 1/s_j, w_j / (s_j sqrt(2 pi))), then Pw[i][j] (zero in the padding).
 // brute_force.py:69-78 (Euler--Maruyama or tme.mean_and_cov on the sub-step ddt) and :84 (norm.pdf * trapz weight).
 // ------------------------------------------------------------------------------------------------------------------
@@ -371,15 +451,30 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   launches += 1;
 
   int cur = 0;
+  // small batches: matrix-vector kernels (the 8-density chunk needs 8 * Kpad doubles of shared memory)
+  const bool use_gemv = chapman && B <= BF_GEMV_MAX_B && (size_t)Kpad * 8 * sizeof(double) <= 200 * 1024;
+  int sms = 148;
+  {
+    int devid = 0;
+    if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
+  }
   const dim3 ggrid((unsigned)(Npad / BF_BN), (unsigned)((B + BF_BM - 1) / BF_BM));
   for (int64_t t = 0; t < a->T; ++t) {
     if (chapman) {
-      for (int k = 0; k < a->integration_steps; ++k) {
-        bf_gemm_kernel<<<ggrid, BF_THREADS, BF_SMEM, s>>>(S[cur], Pw, S[cur ^ 1], B, n, Kpad);
-        cur ^= 1;
+      if (use_gemv) {
+        for (int k = 0; k < a->integration_steps; ++k) {
+          cudaError_t e = gemv_substep(S[cur], Pw, S[cur ^ 1], B, n, Kpad, sms, s, &launches);
+          if (e != cudaSuccess) return fail("brute-force launch failed: %s", cudaGetErrorString(e));
+          cur ^= 1;
+        }
+      } else {
+        for (int k = 0; k < a->integration_steps; ++k) {
+          bf_gemm_kernel<<<ggrid, BF_THREADS, BF_SMEM, s>>>(S[cur], Pw, S[cur ^ 1], B, n, Kpad);
+          cur ^= 1;
+        }
+        BF_CHECK();
+        launches += a->integration_steps;
       }
-      BF_CHECK();
-      launches += a->integration_steps;
     } else {
       BfKolmogorovArgs k;
       k.n = n; k.drift_id = a->drift_id; k.steps = a->integration_steps;

@@ -9,7 +9,8 @@ from ..functors import Drift, Dispersion, TransitionSpec, TransitionFunctor
 
 __all__ = ['sde_cond_moments_tme', 'sde_cond_moments_tme_normal', 'sde_cond_moments_euler',
            'sde_cond_moments_normal_affine', 'raw_moment_of_normal', 'raw_moment_of_standard_normal',
-           'central_moment_of_normal', 'raw_to_central', 'central_to_raw', 'raw_to_scaled', 'scaled_to_central']
+           'central_moment_of_normal', 'raw_to_central', 'central_to_raw', 'raw_to_scaled', 'scaled_to_central',
+           'characteristic_fn']
 
 _ROLES = ('raw', 'central', 'scaled', 'mean', 'mean_var')
 
@@ -117,3 +118,47 @@ def raw_to_scaled(rms, scale=None):
 def scaled_to_central(sms, scale):
     sms = np.asarray(sms, dtype=np.float64)
     return sms * np.asarray(scale, dtype=np.float64)[..., None] ** np.arange(sms.shape[-1])
+
+
+def characteristic_fn(z, ms, mean=0., scale=1.):
+    """Characteristic function by moments, mirror of ``mfs/one_dim/moments.py:309-337``:
+    ``E[exp(i z X)] ~ sum_n w_n exp(i z x_n)`` with ``(w, x) = moment_quadrature(ms, mean, scale)``.
+
+    The reference vmaps this scalar function over the z-grid and the moment history
+    (``dardel/benes_bernoulli/post_processing_mf.py:37-60``); here ``z`` may be a scalar or ``(m,)`` and ``ms``
+    ``(2n,)`` or ``(..., 2n)`` (``mean`` / ``scale`` broadcast against the batch axes): one kernel launch, result
+    ``(..., m)`` complex128 (``(...)`` for scalar ``z``).  torch CUDA ``ms`` -> torch CUDA result, NumPy in -> NumPy out.
+    """
+    import ctypes
+    import torch
+    from .. import _lib
+    is_np = not (isinstance(ms, torch.Tensor) and ms.is_cuda)
+    dev = torch.device('cuda', torch.cuda.current_device()) if is_np else ms.device
+    ms_t = torch.as_tensor(np.asarray(ms, dtype=np.float64) if is_np else ms, dtype=torch.float64, device=dev)
+    n = math.floor(ms_t.shape[-1] / 2)
+    batch_shape = tuple(ms_t.shape[:-1])
+    B = int(np.prod(batch_shape)) if batch_shape else 1
+    ms_c = ms_t[..., :2 * n].reshape(B, 2 * n).contiguous()
+    scalar_z = np.ndim(z) == 0 and not isinstance(z, torch.Tensor)
+    zs = torch.as_tensor(np.atleast_1d(np.asarray(z, dtype=np.float64)) if not isinstance(z, torch.Tensor) else z,
+                         dtype=torch.float64, device=dev).reshape(-1).contiguous()
+    m = int(zs.shape[0])
+
+    def aux(v, default):
+        if np.ndim(v) == 0 and not isinstance(v, torch.Tensor) and float(v) == default:
+            return None
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64) if not isinstance(v, torch.Tensor) else v,
+                            dtype=torch.float64, device=dev)
+        return t.expand(batch_shape).reshape(B).contiguous()
+
+    mean_t, scale_t = aux(mean, 0.), aux(scale, 1.)
+    out = torch.empty((B, m), dtype=torch.complex128, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().mfs_characteristic_fn_1d(
+            n, B, m, ms_c.data_ptr(), None if mean_t is None else mean_t.data_ptr(),
+            None if scale_t is None else scale_t.data_ptr(), zs.data_ptr(), out.data_ptr(), ctypes.c_void_p(stream)))
+    out = out.reshape(batch_shape + (m,))
+    if scalar_z:
+        out = out[..., 0]
+    return out.cpu().numpy() if is_np else out

@@ -18,6 +18,7 @@ reference's code, unmodified, from where it lies:
   mfs/multi_dims/moments.py  Kan--Magnus NumPy branches   -> golden_kan_moments.npz
   mfs/multi_dims/quadratures.py, filtering.py, ss_models.py (prey_predator), utils.GaussianSumND -> golden_nd.npz
   mfs/classical_filters_smoothers/brute_force.py  brute_force_filter -> golden_brute_force.npz
+  mfs/one_dim/moments.py characteristic_fn -> golden_characteristic.npz
   mfs/utils.py ldl_chol through moment_quadrature(ldl=True) / moment_filter_rms(stable=True) -> golden_stable.npz
 
 The third-party ``tme`` package is absent, so fixtures whose transition moments are TME expansions take those
@@ -373,8 +374,30 @@ def golden_stable():
     print('golden_stable.npz', {k: out[k] for k in out if k.endswith('nell')})
 
 
+def golden_characteristic():
+    """mfs/one_dim/moments.py:309-337 characteristic_fn on the shim (100 % reference code): raw / central / scaled
+    moments of the Gaussian mixture, and on filter output (golden_filter_1d_benes_N5 raw moments)."""
+    from mfs.one_dim.moments import characteristic_fn
+    out = {}
+    zs = np.linspace(-6., 6., 41)
+    out['zs'] = zs
+    for N in (3, 5, 8):
+        ic = GaussianSum1D.new(means=jnp.array([-0.5, 0.5]), variances=jnp.array([0.05, 0.05]),
+                               weights=jnp.array([0.5, 0.5]), N=N)
+        for name, (ms, mean, scale) in {'raw': (ic.rms, 0., 1.), 'central': (ic.cms, float(ic.mean), 1.),
+                                        'scaled': (ic.scms, float(ic.mean), float(np.sqrt(ic.variance)))}.items():
+            out[f'mix{N}/{name}/ms'], out[f'mix{N}/{name}/mean'], out[f'mix{N}/{name}/scale'] = np.asarray(ms), mean, scale
+            out[f'mix{N}/{name}/cf'] = np.array([complex(characteristic_fn(z, jnp.asarray(ms), mean, scale)) for z in zs])
+    g = np.load(os.path.join(HERE, 'golden_filter_1d_benes_N5.npz'))
+    rmss = g['tme3/rms/0/rmss'][::10]
+    out['filter/rmss'] = rmss
+    out['filter/cf'] = np.array([[complex(characteristic_fn(z, jnp.asarray(r))) for z in zs] for r in rmss])
+    np.savez_compressed(os.path.join(HERE, 'golden_characteristic.npz'), **out)
+    print('golden_characteristic.npz')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force', 'stable']
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force', 'stable', 'characteristic']
     if 'multi_indices' in which:
         golden_multi_indices()
     if 'nd' in which:
@@ -383,6 +406,8 @@ if __name__ == '__main__':
         golden_brute_force()
     if 'stable' in which:
         golden_stable()
+    if 'characteristic' in which:
+        golden_characteristic()
     if 'quadrature' in which:
         golden_quadrature_1d()
     if 'conversions' in which:

@@ -108,8 +108,8 @@ def test_ragged_sizes_against_oracle(n, B):
 
 
 def test_paper_grid_size_properties():
-    """n = 2000 (dardel/benes_bernoulli/brute_force.py:22), 300 records: unit mass after every update, and the batched
-    run equals record-by-record runs bit for bit (rows of the GEMM are independent)."""
+    """n = 2000 (dardel/benes_bernoulli/brute_force.py:22), 300 records: unit mass after every update; batched (GEMM)
+    and record-by-record (matrix-vector) runs agree."""
     rng = np.random.Generator(np.random.PCG64(681))
     n, B, T, steps = 2000, 300, 3, 4
     xs = np.linspace(-6., 6., n)
@@ -118,9 +118,15 @@ def test_paper_grid_size_properties():
     args = (benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip, xs)
     out = brute_force_filter(*args, ys, 1e-2, integration_steps=steps, pred_method='chapman-tme-3')
     np.testing.assert_allclose(BF.trapz(out.cpu().numpy(), xs), 1., rtol=1e-13)
+    # rows of the contraction are independent: a different batch composition gives the same bits (GEMM path) ...
+    sub = brute_force_filter(*args, ys[100:300], 1e-2, integration_steps=steps, pred_method='chapman-tme-3')
+    np.testing.assert_array_equal(sub.cpu().numpy(), out[100:300].cpu().numpy())
+    # ... and the small-batch matrix-vector path (one record, 5 records) agrees to the summation order
     for k in (0, 127, 128, 299):
         one = brute_force_filter(*args, ys[k], 1e-2, integration_steps=steps, pred_method='chapman-tme-3')
-        np.testing.assert_array_equal(one.cpu().numpy(), out[k].cpu().numpy())
+        _close(one, out[k].cpu().numpy(), rtol=1e-13)
+    five = brute_force_filter(*args, ys[10:15], 1e-2, integration_steps=steps, pred_method='chapman-tme-3')
+    _close(five, out[10:15].cpu().numpy(), rtol=1e-13)
     ref = BF.brute_force_filter('benes', (), 1., lambda y, x: O.bernoulli_pmf(y, 1 / (1 + np.exp(-x ** 3 / 5))), ip, xs,
                                 ys[7], 1e-2, steps, 'chapman-tme-3')
     _close(out[7], ref)

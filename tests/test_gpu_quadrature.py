@@ -75,3 +75,26 @@ def test_quadrature_ldl_negative_pivots_against_reference_golden():
         floor = 2e-14 * np.abs(g[f'quad/{name}/nodes']).max() + 1e-10
         np.testing.assert_allclose(x, g[f'quad/{name}/nodes'], rtol=1e-9, atol=floor)
         np.testing.assert_allclose(w, g[f'quad/{name}/weights'], rtol=1e-8, atol=floor)
+
+
+def test_characteristic_fn_against_reference_golden():
+    """characteristic_fn (mfs/one_dim/moments.py:309-337) vmapped over the z-grid and the moment history like
+    dardel/benes_bernoulli/post_processing_mf.py:37-60: one launch for (T, m)."""
+    from mfs_b200.one_dim.moments import characteristic_fn
+    g = np.load(os.path.join(GOLD, 'golden_characteristic.npz'))
+    zs = g['zs']
+    for N in (3, 5, 8):
+        for name in ('raw', 'central', 'scaled'):
+            cf = characteristic_fn(zs, g[f'mix{N}/{name}/ms'], float(g[f'mix{N}/{name}/mean']),
+                                   float(g[f'mix{N}/{name}/scale']))
+            assert cf.shape == zs.shape and cf.dtype == np.complex128
+            np.testing.assert_allclose(cf, g[f'mix{N}/{name}/cf'], rtol=0, atol=1e-10)
+    cf = characteristic_fn(zs, torch.from_numpy(g['filter/rmss']).cuda())
+    assert cf.is_cuda and cf.shape == g['filter/cf'].shape
+    np.testing.assert_allclose(cf.cpu().numpy(), g['filter/cf'], rtol=0, atol=1e-9)
+    one = characteristic_fn(0.7, g['mix5/raw/ms'])
+    np.testing.assert_allclose(one, np.interp(0.7, zs, g['mix5/raw/cf'].real), atol=2e-2)   # scalar z -> scalar
+    np.testing.assert_allclose(characteristic_fn(0., g['mix5/raw/ms']), 1. + 0.j, atol=1e-13)
+    bad = g['mix5/raw/ms'].copy()
+    bad[2] = bad[1] ** 2 - 1e-3
+    assert np.isnan(characteristic_fn(zs, bad)).all()

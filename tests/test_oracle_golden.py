@@ -192,3 +192,14 @@ def test_stable_golden_negative_pivots():
         # LAPACK builds already differ in the 2nd digit there), so only the likelihood is compared, loosely
         assert np.isfinite(rmss).all() and np.isfinite(g[f'filter/{k}/rmss']).all()
         np.testing.assert_allclose(nell, g[f'filter/{k}/nell'], rtol=1e-4)
+
+
+def test_characteristic_fn_golden():
+    """mfs/one_dim/moments.py:309-337 (reference code on the shim) vs the oracle."""
+    g = np.load(os.path.join(GOLD, 'golden_characteristic.npz'))
+    zs = g['zs']
+    for N in (3, 5, 8):
+        for name in ('raw', 'central', 'scaled'):
+            cf = np.array([O.characteristic_fn(z, g[f'mix{N}/{name}/ms'], float(g[f'mix{N}/{name}/mean']),
+                                               float(g[f'mix{N}/{name}/scale'])) for z in zs])
+            np.testing.assert_allclose(cf, g[f'mix{N}/{name}/cf'], rtol=0, atol=1e-11)
