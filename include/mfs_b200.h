@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MFS_ABI_VERSION 1
+#define MFS_ABI_VERSION 2
 #define MFS_MAX_N 15          /* quadrature nodes; 2N moments.  Reference sweeps N=2..15 (dardel/run_time_profile.sh:25) */
 #define MFS_MAX_PARAMS 4
 
@@ -118,8 +118,17 @@ typedef struct mfs_filter1d_args {
   double* nell_out;      /* [B] negative log-likelihood */
   int32_t* status_out;   /* [B] first failed step or -1; may be NULL */
   int32_t flags;         /* MFS_FLAG_* */
-  int32_t reserved0;
+  int32_t segment_steps; /* segment length of the segmented execution below; 0 = default (64) */
+  /* Optional caller-owned device scratch (size from mfs_filter_1d_workspace_bytes).  With a workspace and T >= 2
+   * segments the scan runs segment by segment and every segment only launches the filters that are still alive,
+   * re-packed densely (a diverged filter otherwise idles its lane -- and its warp -- until the end of the scan).
+   * Results are identical with and without; NULL = one launch for the whole scan. */
+  void* workspace;
+  int64_t workspace_bytes;
 } mfs_filter1d_args;
+
+/* Scratch size in bytes for mfs_filter_1d's segmented execution (-1 for invalid arguments). */
+int64_t mfs_filter_1d_workspace_bytes(int32_t N, int64_t B, int64_t T);
 
 /* ---- d = 2 moment filter (mfs/multi_dims/filtering.py:210-344, quadratures.py:120-178) ------------------------------
  * Moments are ordered graded-lexicographically (mfs/multi_dims/multi_indices.py): position of the multi-index (a, b)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MFS_B200_LIB') or os.path.join(_HERE, 'libmfs_b200.so')   # env override: tuning builds
 CSRC = os.path.join(_HERE, 'csrc')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_N = 15
 MAX_PARAMS = 4
 
@@ -42,7 +42,8 @@ class Filter1dArgs(ctypes.Structure):
         ('ms_out', ctypes.c_void_p), ('ms_stride_b', ctypes.c_int64), ('ms_stride_t', ctypes.c_int64),
         ('mean_out', ctypes.c_void_p), ('scale_out', ctypes.c_void_p), ('aux_stride_b', ctypes.c_int64),
         ('nell_out', ctypes.c_void_p), ('status_out', ctypes.c_void_p),
-        ('flags', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('flags', ctypes.c_int32), ('segment_steps', ctypes.c_int32),
+        ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
     ]
 
 
@@ -84,7 +85,7 @@ BF_METHOD = {'chapman-euler': 0, 'chapman-tme': 1, 'kolmogorov': 2}
 
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
-           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d')
+           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes')
 
 _lib = None
 _lock = threading.Lock()
@@ -124,6 +125,8 @@ def lib() -> ctypes.CDLL:
         L.mfs_functor_lookup.restype = ctypes.c_int
         L.mfs_filter_1d.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_void_p]
         L.mfs_filter_1d.restype = ctypes.c_int
+        L.mfs_filter_1d_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int64]
+        L.mfs_filter_1d_workspace_bytes.restype = ctypes.c_int64
         L.mfs_filter_1d_host.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_int, ctypes.c_int64]
         L.mfs_filter_1d_host.restype = ctypes.c_int
         L.mfs_moment_quadrature_1d.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,

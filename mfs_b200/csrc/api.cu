@@ -67,6 +67,10 @@ static void ws_free(void* p) {
     if (b.ptr == p) { b.busy = false; return; }
 }
 
+}  // namespace mfs
+extern "C" int64_t mfs_filter_1d_workspace_bytes(int32_t N, int64_t B, int64_t T);
+namespace mfs {
+
 static int ys_elem_size(int dtype) { return dtype == MFS_YS_U8 ? 1 : dtype == MFS_YS_I32 ? 4 : 8; }
 
 // Argument checks shared by the device and host entry points (pointer NULL-ness only; both address spaces).
@@ -107,16 +111,18 @@ static int pick_kind(const mfs_filter1d_args& a) {
   return KIND_NORMAL;
 }
 
-static cudaError_t dispatch(const mfs_filter1d_args& a, cudaStream_t s) {
+static cudaError_t dispatch(const mfs_filter1d_args& a, const SegInfo& g, cudaStream_t s) {
   const int kind = pick_kind(a);
   switch (a.N) {
-#define MFS_CASE(n) case n: return launch_filter1d<n>(a, kind, s);
+#define MFS_CASE(n) case n: return launch_filter1d<n>(a, g, kind, s);
     MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
     MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
 #undef MFS_CASE
     default: return cudaErrorInvalidValue;
   }
 }
+
+constexpr int64_t kDefaultSegmentSteps = 64;
 
 static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
   if (a.B == 0) return 0;
@@ -126,9 +132,39 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
       return fail("ms_out must be 16-byte aligned with even strides (vector stores)");
   }
   if (a.B > (int64_t)kBlock * 0x7fffffffLL) return fail("B too large for one launch");
-  cudaError_t e = dispatch(a, s);
-  if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  SegInfo g = {};
+  g.t0 = 0;
+  g.t1 = a.T;
+  const int64_t seg = a.segment_steps > 0 ? a.segment_steps : kDefaultSegmentSteps;
+  if (!a.workspace || a.T < 2 * seg || a.B > 0x7fffffffLL) {     // one launch for the whole scan
+    cudaError_t e = dispatch(a, g, s);
+    if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  // segmented execution with live-filter compaction (filter1d.cuh: SegInfo)
+  const int64_t need = mfs_filter_1d_workspace_bytes(a.N, a.B, a.T);
+  if (a.workspace_bytes < need) return fail("workspace too small: %lld < %lld bytes", (long long)a.workspace_bytes, (long long)need);
+  const int64_t nseg = (a.T + seg - 1) / seg;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(a.workspace) + 255) & ~uintptr_t(255));
+  g.state = reinterpret_cast<double*>(base);
+  const size_t state_bytes = ((size_t)a.B * (4 * a.N + 4) * sizeof(double) + 255) & ~size_t(255);
+  int32_t* idx[2] = {reinterpret_cast<int32_t*>(base + state_bytes),
+                     reinterpret_cast<int32_t*>(base + state_bytes + (((size_t)a.B * 4 + 255) & ~size_t(255)))};
+  int32_t* counts = reinterpret_cast<int32_t*>(base + state_bytes + 2 * (((size_t)a.B * 4 + 255) & ~size_t(255)));
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(nseg + 1), s);
+  if (e != cudaSuccess) return fail("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+  for (int64_t k = 0; k < nseg; ++k) {
+    g.t0 = k * seg;
+    g.t1 = (k + 1 == nseg) ? a.T : (k + 1) * seg;
+    g.idx_in = k == 0 ? nullptr : idx[(k - 1) & 1];
+    g.count_in = k == 0 ? nullptr : counts + k;
+    g.idx_out = (k + 1 == nseg) ? nullptr : idx[k & 1];
+    g.count_out = (k + 1 == nseg) ? nullptr : counts + k + 1;
+    e = dispatch(a, g, s);
+    if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  g_launches.fetch_add(nseg, std::memory_order_relaxed);
   return 0;
 }
 
@@ -266,6 +302,14 @@ int mfs_functor_lookup(const char* kind, const char* name, int32_t* id) {
   return fail("unknown %s functor '%s'", kind, name);
 }
 
+int64_t mfs_filter_1d_workspace_bytes(int32_t N, int64_t B, int64_t T) {
+  if (N < 2 || N > MFS_MAX_N || B < 0 || T < 0) return -1;
+  const int64_t state = ((int64_t)B * (4 * N + 4) * (int64_t)sizeof(double) + 255) & ~int64_t(255);
+  const int64_t idx = ((int64_t)B * 4 + 255) & ~int64_t(255);
+  const int64_t counts = (((T + 1) + 2) * 4 + 255) & ~int64_t(255);   // one counter per segment boundary (<= T + 1)
+  return state + 2 * idx + counts + 256;
+}
+
 int mfs_filter_1d(const mfs_filter1d_args* a, void* stream) {
   if (int rc = validate(a)) return rc;
   return launch_device(*a, static_cast<cudaStream_t>(stream));
@@ -301,6 +345,7 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
     double *ms0 = nullptr, *mean0 = nullptr, *scale0 = nullptr, *tprm = nullptr, *mprm = nullptr;
     double *ms_out = nullptr, *mean_out = nullptr, *scale_out = nullptr, *nell = nullptr;
     int32_t* status = nullptr;
+    void* seg_ws = nullptr;
   } slot[2];
   const bool per_ms0 = a->ms0_stride != 0, per_mean0 = a->mean0 && a->mean0_stride != 0,
              per_scale0 = a->scale0 && a->scale0_stride != 0, per_t = a->trans_param_stride != 0,
@@ -314,6 +359,7 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
       if (k.s) cudaStreamSynchronize(k.s);
       ws_free(k.ys); ws_free(k.ms0); ws_free(k.mean0); ws_free(k.scale0); ws_free(k.tprm); ws_free(k.mprm);
       ws_free(k.ms_out); ws_free(k.mean_out); ws_free(k.scale_out); ws_free(k.nell); ws_free(k.status);
+      ws_free(k.seg_ws);
       if (k.s) cudaStreamDestroy(k.s);
     }
   };
@@ -323,6 +369,9 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
     if (e__ != cudaSuccess) { rc = fail("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return rc; } \
   } while (0)
 
+  // scratch of the segmented execution (live-filter compaction); segment_steps < 0 switches it off
+  const int64_t seg_len = a->segment_steps > 0 ? a->segment_steps : kDefaultSegmentSteps;
+  const int64_t seg_bytes = (a->segment_steps >= 0 && T >= 2 * seg_len) ? mfs_filter_1d_workspace_bytes(a->N, C, T) : 0;
   const int nslots = a->B > C ? 2 : 1;
   for (int k = 0; k < nslots; ++k) {
     Slot& s = slot[k];
@@ -338,6 +387,7 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
     if (out_aux && a->scale_out) MFS_TRY(ws_alloc(device, sizeof(double) * out_aux, reinterpret_cast<void**>(&s.scale_out)));
     MFS_TRY(ws_alloc(device, sizeof(double) * C, reinterpret_cast<void**>(&s.nell)));
     if (a->status_out) MFS_TRY(ws_alloc(device, sizeof(int32_t) * C, reinterpret_cast<void**>(&s.status)));
+    if (seg_bytes > 0) MFS_TRY(ws_alloc(device, (size_t)seg_bytes, &s.seg_ws));
   }
 
   int k = 0;
@@ -365,6 +415,7 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
     d.meas_params = s.mprm; d.meas_param_stride = per_m ? MFS_MAX_PARAMS : 0;
     d.ms_out = s.ms_out; d.mean_out = s.mean_out; d.scale_out = s.scale_out;
     d.nell_out = s.nell; d.status_out = s.status;
+    d.workspace = s.seg_ws; d.workspace_bytes = seg_bytes; d.segment_steps = (int32_t)(seg_bytes > 0 ? seg_len : 0);
     if (per_ms0 && a->ms0_stride != M) { rc = fail("host ms0 must be contiguous (B, 2N)"); cleanup(); return rc; }
     if ((per_t && a->trans_param_stride != MFS_MAX_PARAMS) || (per_m && a->meas_param_stride != MFS_MAX_PARAMS)) {
       rc = fail("host params must be contiguous (B, %d)", MFS_MAX_PARAMS); cleanup(); return rc;

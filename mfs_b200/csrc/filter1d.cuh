@@ -19,6 +19,24 @@ template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
 #endif
 
+// Segmented execution (long horizons).  A filter that loses positive definiteness idles for the rest of the scan, and
+// a warp with one live lane costs as much as a full one; so the host cuts the time axis into segments and every
+// segment runs only the filters that are still alive, re-packed densely: at the end of a segment a live filter parks
+// its state (posterior moments, atoms, mean, scale, nell) in the workspace and appends its id to the next segment's
+// list (warp-aggregated atomic; the order of the list is irrelevant, results are per filter).  No host round-trip:
+// every launch is sized for the initial batch and threads beyond the device-side count exit at once.
+struct SegInfo {
+  const int32_t* idx_in;    // filter ids of this segment (nullptr: identity, first segment / unsegmented)
+  const int32_t* count_in;  // how many ids (nullptr: P.B)
+  int32_t* idx_out;         // ids alive at the end of the segment (nullptr: last segment / unsegmented)
+  int32_t* count_out;
+  double* state;            // [B][4N + 4] parked filter state
+  int64_t t0, t1;           // time steps [t0, t1)
+};
+
+template <int N>
+constexpr int seg_state_doubles() { return 4 * N + 4; }
+
 // Transition kinds the kernel is specialised on (compile time); drift / order / family are runtime switches inside.
 enum { KIND_TME = 0, KIND_NORMAL = 1, KIND_BENES_TME = 2 };
 
@@ -230,16 +248,28 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P) {
-  const int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (b >= P.B) return;
+__global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P, const SegInfo G) {
+  const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t n_active = G.count_in ? (int64_t)__ldg(G.count_in) : P.B;
+  if (slot >= n_active) return;
+  const int64_t b = G.idx_in ? (int64_t)__ldg(G.idx_in + slot) : slot;
+  const bool resume = G.t0 > 0;
+  double* park = G.state ? G.state + b * seg_state_doubles<N>() : nullptr;
 
   double ms[2 * N];
-  const double* ms0 = P.ms0 + b * P.ms0_stride;
+  double mean, scale;
+  if (!resume) {
+    const double* ms0 = P.ms0 + b * P.ms0_stride;
 #pragma unroll
-  for (int p = 0; p < 2 * N; ++p) ms[p] = __ldg(ms0 + p);
-  double mean = (MODE != MFS_MODE_RAW) ? __ldg(P.mean0 + b * P.mean0_stride) : 0.0;
-  double scale = (MODE == MFS_MODE_SCALED) ? __ldg(P.scale0 + b * P.scale0_stride) : 1.0;
+    for (int p = 0; p < 2 * N; ++p) ms[p] = __ldg(ms0 + p);
+    mean = (MODE != MFS_MODE_RAW) ? __ldg(P.mean0 + b * P.mean0_stride) : 0.0;
+    scale = (MODE == MFS_MODE_SCALED) ? __ldg(P.scale0 + b * P.scale0_stride) : 1.0;
+  } else {
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) ms[p] = park[p];
+    mean = (MODE != MFS_MODE_RAW) ? park[4 * N] : 0.0;
+    scale = (MODE == MFS_MODE_SCALED) ? park[4 * N + 1] : 1.0;
+  }
   const double* tprm = P.trans_params + b * P.trans_param_stride;
   const double* mprm = P.meas_params + b * P.meas_param_stride;
   double tp[MFS_MAX_PARAMS], mp[MFS_MAX_PARAMS];
@@ -256,11 +286,17 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   int status = -1;
   double w[N], x[N];          // quadrature of the current half-step; carried across steps as the posterior atoms
   bool have_atoms = false;
-  double y_next = load_y(P.ys, P.ys_dtype, ys_off);
-  int64_t t = 0;
-  for (; t < P.T; ++t) {
+  if (resume) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { w[i] = park[2 * N + i]; x[i] = park[3 * N + i]; }
+    nell = park[4 * N + 2];
+    have_atoms = park[4 * N + 3] != 0.0;
+  }
+  int64_t t = G.t0;
+  double y_next = load_y(P.ys, P.ys_dtype, ys_off + t * P.ys_stride_t);
+  for (; t < G.t1; ++t) {
     const double y = y_next;
-    if (t + 1 < P.T) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
+    if (t + 1 < G.t1) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
 
     // two half-steps sharing ONE instance of the quadrature code: phase 0 = prediction, phase 1 = update.
     // From the second step on, phase 0 re-uses the atoms (x_i, w_i l_i / c) of the previous update as its quadrature.
@@ -317,6 +353,25 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
       }
     }
   }
+  if (status < 0 && G.t1 < P.T) {
+    // alive at the end of a segment: park the state and enlist for the next segment
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) park[p] = ms[p];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { park[2 * N + i] = w[i]; park[3 * N + i] = x[i]; }
+    park[4 * N] = mean;
+    park[4 * N + 1] = scale;
+    park[4 * N + 2] = nell;
+    park[4 * N + 3] = have_atoms ? 1.0 : 0.0;
+    const unsigned peers = __activemask();           // whichever lanes arrive together share one atomic
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(G.count_out, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    G.idx_out[base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)b;
+    return;
+  }
   if (P.out_mode == MFS_OUT_LAST) {
 #pragma unroll
     for (int p = 0; p < 2 * N; p += 2) *reinterpret_cast<double2*>(ms_out + p) = make_double2(ms[p], ms[p + 1]);
@@ -329,6 +384,6 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
 
 // Host-side launcher for one (N, MODE, KIND); defined in filter1d_inst.cu, one translation unit per N.
 template <int N>
-cudaError_t launch_filter1d(const mfs_filter1d_args& a, int kind, cudaStream_t stream);
+cudaError_t launch_filter1d(const mfs_filter1d_args& a, const SegInfo& g, int kind, cudaStream_t stream);
 
 }  // namespace mfs

@@ -8,31 +8,31 @@
 namespace mfs {
 
 template <int N, int MODE, int KIND>
-static cudaError_t launch_one(const mfs_filter1d_args& a, cudaStream_t stream) {
+static cudaError_t launch_one(const mfs_filter1d_args& a, const SegInfo& g, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.B + kBlock - 1) / kBlock);
-  filter1d_kernel<N, MODE, KIND><<<grid, kBlock, 0, stream>>>(a);
+  filter1d_kernel<N, MODE, KIND><<<grid, kBlock, 0, stream>>>(a, g);
   return cudaGetLastError();
 }
 
 template <int N, int MODE>
-static cudaError_t launch_kind(const mfs_filter1d_args& a, int kind, cudaStream_t stream) {
+static cudaError_t launch_kind(const mfs_filter1d_args& a, const SegInfo& g, int kind, cudaStream_t stream) {
   switch (kind) {
-    case KIND_TME: return launch_one<N, MODE, KIND_TME>(a, stream);
+    case KIND_TME: return launch_one<N, MODE, KIND_TME>(a, g, stream);
     case KIND_NORMAL:
       // the reference's scaled Normal factories divide every order by prod(scale**k) (moments.py:205,243): not offered
       if constexpr (MODE == MFS_MODE_SCALED) return cudaErrorInvalidValue;
-      else return launch_one<N, MODE, KIND_NORMAL>(a, stream);
-    case KIND_BENES_TME: return launch_one<N, MODE, KIND_BENES_TME>(a, stream);
+      else return launch_one<N, MODE, KIND_NORMAL>(a, g, stream);
+    case KIND_BENES_TME: return launch_one<N, MODE, KIND_BENES_TME>(a, g, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 template <>
-cudaError_t launch_filter1d<MFS_N>(const mfs_filter1d_args& a, int kind, cudaStream_t stream) {
+cudaError_t launch_filter1d<MFS_N>(const mfs_filter1d_args& a, const SegInfo& g, int kind, cudaStream_t stream) {
   switch (a.mode) {
-    case MFS_MODE_RAW: return launch_kind<MFS_N, MFS_MODE_RAW>(a, kind, stream);
-    case MFS_MODE_CENTRAL: return launch_kind<MFS_N, MFS_MODE_CENTRAL>(a, kind, stream);
-    case MFS_MODE_SCALED: return launch_kind<MFS_N, MFS_MODE_SCALED>(a, kind, stream);
+    case MFS_MODE_RAW: return launch_kind<MFS_N, MFS_MODE_RAW>(a, g, kind, stream);
+    case MFS_MODE_CENTRAL: return launch_kind<MFS_N, MFS_MODE_CENTRAL>(a, g, kind, stream);
+    case MFS_MODE_SCALED: return launch_kind<MFS_N, MFS_MODE_SCALED>(a, g, kind, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -51,7 +51,7 @@ def _ys_dtype_code(dtype_name: str) -> int:
 
 def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stable: bool, history: str,
          device: Optional[int], return_status: bool, chunk_filters: int, out: Optional[dict] = None,
-         recompute_predict_quadrature: bool = False):
+         recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None):
     if history not in _lib.OUT_MODE:
         raise ValueError(f"history must be one of {sorted(_lib.OUT_MODE)}")
     on_device = _is_torch_cuda(ys)
@@ -163,6 +163,13 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
                 scale_out = alloc('scale', aux_shape)
                 a.scale_out = scale_out.data_ptr()
         a.nell_out, a.status_out = nell.data_ptr(), status.data_ptr()
+        # long horizons: scratch for the segmented execution with live-filter compaction (include/mfs_b200.h)
+        seg = 64 if segment_steps is None else int(segment_steps)
+        if seg > 0 and T >= 2 * seg:
+            ws_bytes = int(L.mfs_filter_1d_workspace_bytes(N, B, T))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            keep.append(ws)
+            a.segment_steps, a.workspace, a.workspace_bytes = seg, ws.data_ptr(), ws_bytes
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(L.mfs_filter_1d(ctypes.byref(a), ctypes.c_void_p(stream)))
@@ -214,6 +221,7 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
         if device is None:
             import torch
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        a.segment_steps = -1 if (segment_steps is not None and int(segment_steps) <= 0) else int(segment_steps or 0)
         _lib.check(L.mfs_filter_1d_host(ctypes.byref(a), int(device), int(chunk_filters)))
         reshape = lambda t, tail: None if t is None else t.reshape(batch_shape + tail)
 
@@ -231,7 +239,7 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
 def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, stable: bool = False, *,
                       history: str = 'full', device: Optional[int] = None, return_status: bool = False,
                       chunk_filters: int = 0, out: Optional[dict] = None,
-                      recompute_predict_quadrature: bool = False):
+                      recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None):
     """Raw-moment filter, mirror of ``mfs/one_dim/filtering.py:32-89``.
 
     Returns ``(rmss (..., T, 2N), nell (...))`` like the reference (``history='last'`` -> ``(..., 2N)``,
@@ -244,10 +252,14 @@ def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, st
     per step, ``filtering.py:78``).  By default the prediction half-step re-uses the posterior atoms
     ``{x_i, w_i p(y|x_i)/c}`` of the previous update -- the N-point Gauss rule of an N-atom measure is the measure
     itself -- while still testing the Hankel pivots of the posterior moments, so NaN-on-non-PD fires identically.
+
+    Long horizons (``T >= 2 * segment_steps``, default 64) run segment by segment, each segment launching only the
+    filters that are still alive, densely re-packed (a diverged filter would otherwise idle its warp until the end of
+    the scan); results are identical.  ``segment_steps=0`` runs the whole scan in one launch.
     """
     fn = _check_transition(state_cond_raw_moments, 'raw', 'state_cond_raw_moments')
     out = _run('raw', fn.spec, _check_measurement(measurement_cond_pdf), rms0, None, None, ys, stable, history,
-               device, return_status, chunk_filters, out, recompute_predict_quadrature)
+               device, return_status, chunk_filters, out, recompute_predict_quadrature, segment_steps)
     res = (out['ms'], out['nell'])
     return res + (out['status'],) if return_status else res
 
@@ -255,14 +267,14 @@ def moment_filter_rms(state_cond_raw_moments, measurement_cond_pdf, rms0, ys, st
 def moment_filter_cms(state_cond_central_moments, state_cond_mean, measurement_cond_pdf, cms0, mean0, ys,
                       stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
                       return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None,
-                      recompute_predict_quadrature: bool = False):
+                      recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None):
     """Central-moment filter, mirror of ``mfs/one_dim/filtering.py:92-161``.  Returns ``(cmss, means, nell)``."""
     fn = _check_transition(state_cond_central_moments, 'central', 'state_cond_central_moments')
     fm = _check_transition(state_cond_mean, 'mean', 'state_cond_mean')
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_central_moments and state_cond_mean must come from the same factory call')
     out = _run('central', fn.spec, _check_measurement(measurement_cond_pdf), cms0, mean0, None, ys, stable, history,
-               device, return_status, chunk_filters, out, recompute_predict_quadrature)
+               device, return_status, chunk_filters, out, recompute_predict_quadrature, segment_steps)
     res = (out['ms'], out['mean'], out['nell'])
     return res + (out['status'],) if return_status else res
 
@@ -270,7 +282,7 @@ def moment_filter_cms(state_cond_central_moments, state_cond_mean, measurement_c
 def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, measurement_cond_pdf, scms0, mean0,
                        scale0, ys, stable: bool = False, *, history: str = 'full', device: Optional[int] = None,
                        return_status: bool = False, chunk_filters: int = 0, out: Optional[dict] = None,
-                      recompute_predict_quadrature: bool = False):
+                       recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None):
     """Scaled-central-moment filter, mirror of ``mfs/one_dim/filtering.py:164-240``.
     Returns ``(scmss, means, scales, nell)``."""
     fn = _check_transition(state_cond_scaled_central_moments, 'scaled', 'state_cond_scaled_central_moments')
@@ -278,6 +290,6 @@ def moment_filter_scms(state_cond_scaled_central_moments, state_cond_mean_var, m
     if fm.spec is not fn.spec:
         raise ValueError('state_cond_scaled_central_moments and state_cond_mean_var must come from the same factory')
     out = _run('scaled', fn.spec, _check_measurement(measurement_cond_pdf), scms0, mean0, scale0, ys, stable,
-               history, device, return_status, chunk_filters, out, recompute_predict_quadrature)
+               history, device, return_status, chunk_filters, out, recompute_predict_quadrature, segment_steps)
     res = (out['ms'], out['mean'], out['scale'], out['nell'])
     return res + (out['status'],) if return_status else res
