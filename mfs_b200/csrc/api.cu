@@ -122,6 +122,32 @@ static cudaError_t dispatch(const mfs_filter1d_args& a, const SegInfo& g, cudaSt
   }
 }
 
+// NaN tails of the filters that failed (JAX semantics: everything after a failed Cholesky is NaN until the end of the
+// scan).  Written here, one warp per failed filter with coalesced stores, instead of by the failing thread itself --
+// which would hold its whole warp for up to T - t serial store rounds.
+__global__ void __launch_bounds__(128) nan_fill_kernel(const mfs_filter1d_args P) {
+  const int64_t b = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= P.B) return;
+  const int s = P.status_out[b];
+  if (s < 0) return;
+  const int M = 2 * P.N;
+  const double qnan = nan("");
+  double* o = P.ms_out + b * P.ms_stride_b;
+  if (P.ms_stride_t == M) {
+    double* base = o + (int64_t)s * M;
+    const int64_t cnt = (P.T - s) * M;
+    for (int64_t e = lane; e < cnt; e += 32) base[e] = qnan;
+  } else {
+    for (int64_t t = s; t < P.T; ++t)
+      for (int p = lane; p < M; p += 32) o[t * P.ms_stride_t + p] = qnan;
+  }
+  if (P.mode != MFS_MODE_RAW && P.mean_out)
+    for (int64_t t = s + lane; t < P.T; t += 32) P.mean_out[b * P.aux_stride_b + t] = qnan;
+  if (P.mode == MFS_MODE_SCALED && P.scale_out)
+    for (int64_t t = s + lane; t < P.T; t += 32) P.scale_out[b * P.aux_stride_b + t] = qnan;
+}
+
 constexpr int64_t kDefaultSegmentSteps = 64;
 
 static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
@@ -135,12 +161,23 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
   SegInfo g = {};
   g.t0 = 0;
   g.t1 = a.T;
+  g.defer_nan_fill = (a.out_mode == MFS_OUT_FULL && a.status_out != nullptr && a.T > 1) ? 1 : 0;
+  auto fill_tails = [&]() -> int {
+    if (!g.defer_nan_fill) return 0;
+    const int64_t ctas = (a.B * 32 + 127) / 128;
+    if (ctas > 0x7fffffffLL) return fail("B too large for the NaN-tail launch");
+    nan_fill_kernel<<<(unsigned)ctas, 128, 0, s>>>(a);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return fail("nan_fill launch failed: %s", cudaGetErrorString(e2));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  };
   const int64_t seg = a.segment_steps > 0 ? a.segment_steps : kDefaultSegmentSteps;
   if (!a.workspace || a.T < 2 * seg || a.B > 0x7fffffffLL) {     // one launch for the whole scan
     cudaError_t e = dispatch(a, g, s);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return 0;
+    return fill_tails();
   }
   // segmented execution with live-filter compaction (filter1d.cuh: SegInfo)
   const int64_t need = mfs_filter_1d_workspace_bytes(a.N, a.B, a.T);
@@ -165,7 +202,7 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   }
   g_launches.fetch_add(nseg, std::memory_order_relaxed);
-  return 0;
+  return fill_tails();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

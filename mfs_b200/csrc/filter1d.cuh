@@ -32,6 +32,7 @@ struct SegInfo {
   int32_t* count_out;
   double* state;            // [B][4N + 4] parked filter state
   int64_t t0, t1;           // time steps [t0, t1)
+  int32_t defer_nan_fill;   // 1: a failing filter only records its status; nan_fill_kernel writes the NaN tails
 };
 
 template <int N>
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
     for (int p = 0; p < 2 * N; ++p) ms[p] = qnan;
     mean = qnan;
     scale = qnan;
-    if (P.out_mode == MFS_OUT_FULL) {
+    if (P.out_mode == MFS_OUT_FULL && !G.defer_nan_fill) {
       for (; t < P.T; ++t) {
         double* o = ms_out + t * P.ms_stride_t;
 #pragma unroll
