@@ -284,6 +284,15 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     qd[S - 1] = __shfl_sync(kFull, a[S - 1], gbase + S - 1);
     qe[S - 1] = 0.0;
     // ---- D
+    // Large S: the V rows go to shared memory and the chase below is a ROLLED loop (run-time index) of ~100
+    // instructions that stays in the instruction cache, instead of S-1 unrolled bodies (22 KB at S = 15) re-fetched
+    // every sweep (measured: +8 % at N = 5, -4 % at N = 3, 4 -- profiles/r1_nd_occupancy.md).
+    constexpr bool kRolled = S >= 15;
+    double* Vr = V + k * SS + cc * S;
+    if (kRolled && act) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) Vr[c] = z[c];
+    }
     unsigned neg = 1u << (S - 1);            // bit i <=> coupling e[i] negligible; bit S-1 is a sentinel
 #pragma unroll
     for (int i = 0; i + 1 < S; ++i)
@@ -317,38 +326,53 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
       }
       bool stop = done;
       double d_below = 0.0;                  // d[i+2] as left by the previous rotation
-#pragma unroll
-      for (int i = S - 2; i >= 0; --i) {
-        if (i < lo) break;
-        if (i < hi && !stop && i < m && i >= l) {
-          const double e_i = qe[i], d_i = qd[i], d_up = qd[i + 1];
-          const double f = sn * e_i, b = cs * e_i;
-          const double h2 = fma(f, f, g * g);
-          if (h2 == 0.0) {                   // underflow: the matrix splits here
-            qd[i + 1] = d_up - pp;
-            qe[i + 1] = 0.0;
-            neg |= 1u << (i + 1);
-            stop = true;
+      auto rotate = [&](const int i) {
+        const double e_i = qe[i], d_i = qd[i], d_up = qd[i + 1];
+        const double f = sn * e_i, b = cs * e_i;
+        const double h2 = fma(f, f, g * g);
+        if (h2 == 0.0) {                     // underflow: the matrix splits here
+          qd[i + 1] = d_up - pp;
+          qe[i + 1] = 0.0;
+          neg |= 1u << (i + 1);
+          stop = true;
+        } else {
+          const double rinv = rsqrt_fast(h2);
+          const double e_new = h2 * rinv;
+          qe[i + 1] = e_new;
+          sn = f * rinv;
+          cs = g * rinv;
+          g = d_up - pp;
+          const double rr = fma(d_i - g, sn, (cs + cs) * b);
+          pp = sn * rr;
+          const double d_new = g + pp;
+          qd[i + 1] = d_new;
+          g = fma(cs, rr, -b);
+          if constexpr (kRolled) {
+            if (act) {
+              const double z1 = Vr[i + 1], z0 = Vr[i];
+              Vr[i + 1] = fma(sn, z0, cs * z1);
+              Vr[i] = fma(cs, z0, -sn * z1);
+            }
           } else {
-            const double rinv = rsqrt_fast(h2);
-            const double e_new = h2 * rinv;
-            qe[i + 1] = e_new;
-            sn = f * rinv;
-            cs = g * rinv;
-            g = d_up - pp;
-            const double rr = fma(d_i - g, sn, (cs + cs) * b);
-            pp = sn * rr;
-            const double d_new = g + pp;
-            qd[i + 1] = d_new;
-            g = fma(cs, rr, -b);
             const double z1 = z[i + 1];
             z[i + 1] = fma(sn, z[i], cs * z1);
             z[i] = fma(cs, z[i], -sn * z1);
-            // e[i+1] and d[i+1], d[i+2] are final for this sweep: refresh the negligibility bit
-            const bool small = e_new <= kEps * (fabs(d_new) + fabs(d_below));
-            neg = small ? (neg | (1u << (i + 1))) : (neg & ~(1u << (i + 1)));
-            d_below = d_new;
           }
+          // e[i+1] and d[i+1], d[i+2] are final for this sweep: refresh the negligibility bit
+          const bool small = e_new <= kEps * (fabs(d_new) + fabs(d_below));
+          neg = small ? (neg | (1u << (i + 1))) : (neg & ~(1u << (i + 1)));
+          d_below = d_new;
+        }
+      };
+      if constexpr (kRolled) {
+#pragma unroll 1
+        for (int i = hi - 1; i >= lo; --i)
+          if (!stop && i < m && i >= l) rotate(i);
+      } else {
+#pragma unroll
+        for (int i = S - 2; i >= 0; --i) {
+          if (i < lo) break;
+          if (i < hi && !stop && i < m && i >= l) rotate(i);
         }
       }
       if (!done) {
@@ -364,7 +388,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
       }
     }
     if (bad) fail = 1;
-    if (act) {
+    if (!kRolled && act) {
 #pragma unroll
       for (int c = 0; c < S; ++c) V[k * SS + r * S + c] = z[c];
     }
