@@ -250,6 +250,10 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND>
 __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P, const SegInfo G) {
+#ifdef MFS_QL_SMEM
+  extern __shared__ double ql_smem[];                 // [3N][kBlock]: (d, e, z) of the eigen-solve, one column per thread
+  double* const ql_tile = ql_smem + threadIdx.x;
+#endif
   const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t n_active = G.count_in ? (int64_t)__ldg(G.count_in) : P.B;
   if (slot >= n_active) return;
@@ -309,7 +313,11 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
         double dj[N], ej[N];
         ok = jacobi_from_moments<N, false>(ms, dj, ej);
         if (ok) {
+#ifdef MFS_QL_SMEM
+          if (!(phase == 0 && have_atoms)) ok = jacobi_to_rule_smem<N, kBlock>(dj, ej, mean, scale, w, x, ql_tile);
+#else
           if (!(phase == 0 && have_atoms)) ok = jacobi_to_rule<N>(dj, ej, mean, scale, w, x);
+#endif
         } else if (P.stable) {
           // stable=True: a non-positive pivot is not a failure but the LDL completion of mfs/utils.py:526-538
           ok = moment_quadrature_stable_fallback<N>(ms, mean, scale, w, x);

@@ -10,7 +10,18 @@ namespace mfs {
 template <int N, int MODE, int KIND>
 static cudaError_t launch_one(const mfs_filter1d_args& a, const SegInfo& g, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.B + kBlock - 1) / kBlock);
+#ifdef MFS_QL_SMEM
+  const size_t smem = sizeof(double) * 3 * N * kBlock;
+  static bool configured = false;   // benign race: the attribute is idempotent
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(filter1d_kernel<N, MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  filter1d_kernel<N, MODE, KIND><<<grid, kBlock, smem, stream>>>(a, g);
+#else
   filter1d_kernel<N, MODE, KIND><<<grid, kBlock, 0, stream>>>(a, g);
+#endif
   return cudaGetLastError();
 }
 
