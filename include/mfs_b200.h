@@ -155,7 +155,7 @@ typedef struct mfs_filternd_args {
   const uint8_t* ys;                                        /* [B][T] */
   const int32_t* inds;                                      /* [3][s][s] */
   int32_t out_mode;      /* MFS_OUT_* */
-  int32_t reserved0;
+  int32_t stable;        /* 0/1: `stable=True`, LDL completion of the Gram factor (mfs/utils.py:526-538) */
   double* ms_out;        /* FULL [B][T][z] | LAST [B][z] */
   double* mean_out;      /* FULL [B][T][2] | LAST [B][2] */
   double* nell_out;      /* [B] */
@@ -238,6 +238,13 @@ int mfs_release_cached_memory(void);
  * nodes when sort_nodes != 0).  mean/scale may be NULL (0 / 1).  Device pointers. */
 int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
                              int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream);
+
+/* Batched d-dimensional moment quadrature (mfs/multi_dims/quadratures.py:120-178), d = 2, N = 2..6:
+ * ms[B][z] (graded-lex order, z = N(2N+1)) -> weights[B][S^2], nodes[B][S^2][2], S = N(N+1)/2, in the reference's
+ * Cartesian order (node i*S + j = (lambda1_i, lambda2_j)).  mean / scale: [B][2] or NULL; inds: the (3, S, S) int32
+ * table of gram_and_hankel_indices_graded_lexico(N, 2); ldl != 0: `ldl=True`.  Device pointers.  Failure -> NaN. */
+int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, const double* mean, const double* scale,
+                             const int32_t* inds, int32_t ldl, double* weights, double* nodes, void* stream);
 
 /* Characteristic function by moments (mfs/one_dim/moments.py:309-337), the post-processing step after the filter
  * (dardel/benes_bernoulli/post_processing_mf.py:37-60): out[b][j] = sum_n w_n exp(i zs[j] x_n) with (w, x) the

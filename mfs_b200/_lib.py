@@ -59,7 +59,7 @@ class FilterNdArgs(ctypes.Structure):
         ('ms0', ctypes.c_void_p), ('ms0_stride', ctypes.c_int64),
         ('mean0', ctypes.c_void_p), ('mean0_stride', ctypes.c_int64),
         ('ys', ctypes.c_void_p), ('inds', ctypes.c_void_p),
-        ('out_mode', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('out_mode', ctypes.c_int32), ('stable', ctypes.c_int32),
         ('ms_out', ctypes.c_void_p), ('mean_out', ctypes.c_void_p), ('nell_out', ctypes.c_void_p),
         ('status_out', ctypes.c_void_p),
     ]
@@ -85,7 +85,7 @@ BF_METHOD = {'chapman-euler': 0, 'chapman-tme': 1, 'kolmogorov': 2}
 
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
-           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes')
+           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd')
 
 _lib = None
 _lock = threading.Lock()
@@ -144,6 +144,10 @@ def lib() -> ctypes.CDLL:
         L.mfs_dmma_peak.restype = ctypes.c_int
         L.mfs_characteristic_fn_1d.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 6
         L.mfs_characteristic_fn_1d.restype = ctypes.c_int
+        L.mfs_moment_quadrature_nd.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.mfs_moment_quadrature_nd.restype = ctypes.c_int
         L.mfs_launch_count.restype = ctypes.c_int64
         L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]

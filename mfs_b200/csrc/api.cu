@@ -536,7 +536,7 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
   if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
   NdArgs k;
   k.mode = a->mode; k.trans_id = a->trans_id; k.tme_order = a->tme_order; k.meas_id = a->meas_id; k.obs_dim = a->obs_dim;
-  k.out_mode = a->out_mode; k.B = a->B; k.T = a->T; k.dt = a->dt;
+  k.out_mode = a->out_mode; k.stable = a->stable ? 1 : 0; k.B = a->B; k.T = a->T; k.dt = a->dt;
   k.trans_params = a->trans_params; k.trans_param_stride = a->trans_param_stride;
   k.meas_params = a->meas_params; k.meas_param_stride = a->meas_param_stride;
   k.ms0 = a->ms0; k.ms0_stride = a->ms0_stride; k.mean0 = a->mean0; k.mean0_stride = a->mean0_stride;
@@ -552,6 +552,29 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
     case 6: e = launch_filter_nd<6>(k, s); break;
   }
   if (e != cudaSuccess) return fail("2-D filter launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, const double* mean, const double* scale,
+                             const int32_t* inds, int32_t ldl, double* weights, double* nodes, void* stream) {
+  if (d != 2) return fail("only d = 2 is implemented (got d = %d)", d);
+  if (N < 2 || N > 6) return fail("N=%d outside [2, 6] for the 2-D quadrature", N);
+  if (B < 0) return fail("negative B");
+  if (B == 0) return 0;
+  if (!ms || !inds || !weights || !nodes) return fail("NULL pointer argument");
+  NdQuadArgs q;
+  q.B = B; q.ms = ms; q.mean = mean; q.scale = scale; q.inds = inds; q.stable = ldl ? 1 : 0; q.weights = weights; q.nodes = nodes;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (N) {
+    case 2: e = launch_quadrature_nd<2>(q, s); break;
+    case 3: e = launch_quadrature_nd<3>(q, s); break;
+    case 4: e = launch_quadrature_nd<4>(q, s); break;
+    case 5: e = launch_quadrature_nd<5>(q, s); break;
+    case 6: e = launch_quadrature_nd<6>(q, s); break;
+  }
+  if (e != cudaSuccess) return fail("2-D quadrature launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -27,6 +27,7 @@ struct NdArgs {
   int32_t meas_id;     // MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC on x[obs_dim]
   int32_t obs_dim;
   int32_t out_mode;
+  int32_t stable;      // 1: LDL completion of the Gram factor (mfs/utils.py:526-538) instead of NaN on a non-positive pivot
   int64_t B, T;
   double dt;
   const double* trans_params;  // {alpha, beta, delta, gamma, sigma}
@@ -142,7 +143,7 @@ struct NdDims {
 //   after the other with all 32 lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N>
-__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane) {   // one copy, two call sites
+__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable) {   // one copy, two call sites
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
   constexpr unsigned kFull = 0xffffffffu;
@@ -162,17 +163,42 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     double g[S];
 #pragma unroll
     for (int c = 0; c < S; ++c) g[c] = ms[tab[rr * S + c]];
+    if (!stable) {
 #pragma unroll
-    for (int j = 0; j < S; ++j) {
-      const double piv = __shfl_sync(kFull, g[j], j);
-      if (!(piv > 0.0)) return 1;
-      const double rinv = rsqrt_fast(piv);
-      rdi[j] = rinv;
-      g[j] *= rinv;                                   // L[r][j] for r >= j
+      for (int j = 0; j < S; ++j) {
+        const double piv = __shfl_sync(kFull, g[j], j);
+        if (!(piv > 0.0)) return 1;
+        const double rinv = rsqrt_fast(piv);
+        rdi[j] = rinv;
+        g[j] *= rinv;                                   // L[r][j] for r >= j
 #pragma unroll
-      for (int c = j + 1; c < S; ++c) {
-        const double lcj = __shfl_sync(kFull, g[j], c);
-        g[c] = fma(-g[j], lcj, g[c]);                 // only the entries c <= r are ever used
+        for (int c = j + 1; c < S; ++c) {
+          const double lcj = __shfl_sync(kFull, g[j], c);
+          g[c] = fma(-g[j], lcj, g[c]);                 // only the entries c <= r are ever used
+        }
+      }
+    } else {
+      // `stable=True` (quadratures.py:152 with ldl=True): LDL^T without pivoting and the factor
+      // L diag(where(d < 0, 1e-8 ||G||_F, sqrt(d)))  (mfs/utils.py:515-538); d == 0 gives inf/NaN like the reference.
+      double fro = 0.0;
+#pragma unroll
+      for (int c = 0; c < S; ++c) fro = fma(g[c], g[c], fro);
+      fro = warp_sum((lane < S) ? fro : 0.0);
+      const double eps = 1e-8 * sqrt(fro);
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const double piv = __shfl_sync(kFull, g[j], j);                  // d_j
+        if (!(piv == piv)) return 1;
+        const double sj = (piv < 0.0) ? eps : sqrt(piv);
+        rdi[j] = 1.0 / sj;
+        const double gj = g[j];                                          // l_rj d_j
+        const double lj = gj / piv;                                      // l_rj (1 on the diagonal)
+#pragma unroll
+        for (int c = j + 1; c < S; ++c) {
+          const double gcj = __shfl_sync(kFull, gj, c);                  // l_cj d_j
+          g[c] = fma(-lj, gcj, g[c]);
+        }
+        g[j] = lj * sj;                                                  // R[r][j]
       }
     }
     if (lane < S) {
@@ -550,7 +576,7 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
   for (; t < P.T; ++t) {
     const double y = (double)__ldg(P.ys + b * P.T + t);
     // ---------------- prediction ----------------
-    int why = quadrature_nd<N>(sm, tab, lane);
+    int why = quadrature_nd<N>(sm, tab, lane, P.stable);
     if (why) { status = (int)t; reason = why; break; }
     double acc[Z];
     const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
@@ -587,7 +613,7 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
     __syncwarp();
     warp_reduce_moments<N>(acc, scratch, ms, 1.0, lane);
     // ---------------- update ----------------
-    why = quadrature_nd<N>(sm, tab, lane);
+    why = quadrature_nd<N>(sm, tab, lane, P.stable);
     if (why) { status = (int)t; reason = why + 4; break; }
     MeasStep st;
     st.y = y;
@@ -669,6 +695,50 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
     if (P.status_out) P.status_out[b] = status;
   }
 }
+
+// Batched moment_quadrature_nd (mfs/multi_dims/quadratures.py:120-178) as an API of its own: one warp per moment vector,
+// the same quadrature_nd<N> as inside the filter.  weights [B][S^2], nodes [B][S^2][2] in the reference's Cartesian
+// order (node e = i S + j is (lambda1_i, lambda2_j); the order / signs within each eigen-decomposition are arbitrary).
+struct NdQuadArgs {
+  int64_t B;
+  const double* ms;     // [B][z]
+  const double* mean;   // [B][2] or nullptr
+  const double* scale;  // [B][2] or nullptr
+  const int32_t* inds;  // [3][S][S]
+  int32_t stable;
+  double* weights;
+  double* nodes;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) quadrature_nd_kernel(const NdQuadArgs P) {
+  using D = NdDims<N>;
+  constexpr int S = D::S, SS = D::SS, Z = D::Z;
+  extern __shared__ double smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kNdWarps + warp;
+  int* tab = reinterpret_cast<int*>(smem_all + kNdWarps * D::kDoubles);
+  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = __ldg(P.inds + e);
+  __syncthreads();
+  if (b >= P.B) return;
+  double* sm = smem_all + warp * D::kDoubles;
+  double* wts = sm + Z + 5 * SS;
+  double* lam = wts + SS;
+  for (int e = lane; e < Z; e += 32) sm[e] = __ldg(P.ms + b * Z + e);
+  __syncwarp();
+  const int why = quadrature_nd<N>(sm, tab, lane, P.stable);
+  const double m1 = P.mean ? P.mean[b * 2] : 0.0, m2 = P.mean ? P.mean[b * 2 + 1] : 0.0;
+  const double s1 = P.scale ? P.scale[b * 2] : 1.0, s2 = P.scale ? P.scale[b * 2 + 1] : 1.0;
+  const double qnan = nan("");
+  for (int e = lane; e < SS; e += 32) {
+    P.weights[b * SS + e] = why ? qnan : wts[e];
+    P.nodes[(b * SS + e) * 2] = why ? qnan : fma(s1, lam[e / S], m1);
+    P.nodes[(b * SS + e) * 2 + 1] = why ? qnan : fma(s2, lam[S + e % S], m2);
+  }
+}
+
+template <int N>
+cudaError_t launch_quadrature_nd(const NdQuadArgs& a, cudaStream_t stream);
 
 template <int N>
 cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream);

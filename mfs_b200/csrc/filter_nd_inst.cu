@@ -18,6 +18,27 @@ cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <int N>
+cudaError_t launch_quadrature_nd(const NdQuadArgs& a, cudaStream_t stream) {
+  using D = NdDims<N>;
+  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
+  static bool configured = false;   // benign race: the attribute is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(quadrature_nd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((a.B + kNdWarps - 1) / kNdWarps);
+  quadrature_nd_kernel<N><<<grid, kNdWarps * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template cudaError_t launch_quadrature_nd<2>(const NdQuadArgs&, cudaStream_t);
+template cudaError_t launch_quadrature_nd<3>(const NdQuadArgs&, cudaStream_t);
+template cudaError_t launch_quadrature_nd<4>(const NdQuadArgs&, cudaStream_t);
+template cudaError_t launch_quadrature_nd<5>(const NdQuadArgs&, cudaStream_t);
+template cudaError_t launch_quadrature_nd<6>(const NdQuadArgs&, cudaStream_t);
+
 template cudaError_t launch_filter_nd<2>(const NdArgs&, cudaStream_t);
 template cudaError_t launch_filter_nd<3>(const NdArgs&, cudaStream_t);
 template cudaError_t launch_filter_nd<4>(const NdArgs&, cudaStream_t);

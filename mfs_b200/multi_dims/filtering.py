@@ -36,8 +36,6 @@ def _check(fn_and_flag, role):
 
 def _run(mode, spec, meas, ys, moments_partial_order, ms0, mean0, stable, history, return_status):
     import torch
-    if stable:
-        raise _lib.MfsError('stable=True is not implemented for the d-dimensional filter in this build')
     if not isinstance(meas, MeasurementFunctor) or meas.name != 'bernoulli_logistic_cubic':
         raise TypeError('measurement_cond_pdf must be the bernoulli_logistic_cubic MeasurementFunctor handle')
     multi_indices, inds = moments_partial_order
@@ -95,6 +93,7 @@ def _run(mode, spec, meas, ys, moments_partial_order, ms0, mean0, stable, histor
         keep.append(mean0_t)
     a.ys, a.inds = ys_c.data_ptr(), inds_t.data_ptr()
     a.out_mode = _lib.OUT_MODE[history]
+    a.stable = int(bool(stable))
     f64 = dict(dtype=torch.float64, device=dev)
     nell = torch.empty(B, **f64)
     status = torch.empty(B, dtype=torch.int32, device=dev)

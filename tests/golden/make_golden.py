@@ -370,6 +370,22 @@ def golden_stable():
     for k in range(2):
         rmss, nell = moment_filter_rms(e_rms, pmf, jnp.asarray(bad), jnp.asarray(ys_all[k]), stable=True)
         out[f'filter/{k}/rmss'], out[f'filter/{k}/nell'] = np.asarray(rmss), float(nell)
+    # d = 2: moment_quadrature_nd(ldl=True) on a Gram matrix with a negative pivot (quadratures.py:152)
+    from mfs.multi_dims.multi_indices import (generate_graded_lexico_multi_indices,
+                                              gram_and_hankel_indices_graded_lexico)
+    from mfs.multi_dims.quadratures import moment_quadrature_nd
+    from mfs.multi_dims.moments import raw_moments_mvn_kan
+    mean, cov = np.array([0.3, -0.2]), np.array([[1.1, 0.3], [0.3, 0.7]])
+    for Nn in (2, 3):
+        mis = generate_graded_lexico_multi_indices(2, 2 * Nn - 1, 0)
+        inds = gram_and_hankel_indices_graded_lexico(Nn, 2)
+        rms = np.array([raw_moments_mvn_kan(mean, cov, n) for n in mis])
+        bad = rms.copy()
+        bad[int(np.where((mis == [2, 0]).all(axis=1))[0][0])] *= 0.2          # E[x1^2] too small: negative pivot
+        w, x = moment_quadrature_nd(jnp.asarray(bad), inds, ldl=True)
+        out[f'nd/N{Nn}/ms'], out[f'nd/N{Nn}/w'], out[f'nd/N{Nn}/x'] = bad, np.asarray(w), np.asarray(x)
+        w, x = moment_quadrature_nd(jnp.asarray(rms), inds, ldl=True)
+        out[f'nd/N{Nn}/ms_pd'], out[f'nd/N{Nn}/w_pd'], out[f'nd/N{Nn}/x_pd'] = rms, np.asarray(w), np.asarray(x)
     np.savez_compressed(os.path.join(HERE, 'golden_stable.npz'), **out)
     print('golden_stable.npz', {k: out[k] for k in out if k.endswith('nell')})
 

@@ -134,3 +134,56 @@ def test_tme_without_normal_approximation_against_oracle(N, order):
             if np.isfinite(ref_n) and st[k].item() < 0:
                 np.testing.assert_allclose(rmss[k].cpu().numpy(), ref_r, rtol=1e-6)
                 np.testing.assert_allclose(nell_r[k].item(), ref_n, rtol=1e-7)
+
+
+def _canon(w, x):
+    """sort the nodes lexicographically (the eigenpair order of an eigh is arbitrary)"""
+    order = np.lexsort((x[:, 1], x[:, 0]))
+    return w[order], x[order]
+
+
+def _same_measure(w, x, wr, xr, tol=1e-9):
+    """K_1 / K_2 of a product-like measure have REPEATED eigenvalues, so the eigenvectors -- and with them the split of
+    the weight among coincident nodes -- depend on the eigen-solver; the discrete measure sum_e w_e delta(x_e) does not.
+    Compare it through a family of bounded test functions."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    for _ in range(24):
+        a, b = rng.normal(size=2), rng.uniform(0, 2 * np.pi)
+        np.testing.assert_allclose(np.dot(w, np.cos(x @ a + b)), np.dot(wr, np.cos(xr @ a + b)), rtol=0, atol=tol)
+
+
+def test_moment_quadrature_nd_against_reference_golden():
+    """mfs/multi_dims/quadratures.py:120-178 (reference code on the shim, golden_nd.npz): correlated Gaussian, raw and
+    central moments, N = 3, 4, 5; plus `ldl=True` (golden_stable.npz)."""
+    from mfs_b200.multi_dims.quadratures import moment_quadrature_nd
+    g = np.load(os.path.join(GOLD, 'golden_nd.npz'))
+    for N in (3, 4, 5):
+        inds = gram_and_hankel_indices_graded_lexico(N, 2)
+        for tag, ms, mean in (('', g[f'quad/N{N}/rms'], None), ('c', g[f'quad/N{N}/cms'], g['quad/mean'])):
+            w, x = moment_quadrature_nd(ms, inds, mean)
+            wr, xr = g[f'quad/N{N}/w{tag}'], g[f'quad/N{N}/x{tag}']
+            assert w.shape == wr.shape and x.shape == xr.shape
+            (w, x), (wr, xr) = _canon(w, x), _canon(wr, xr)
+            np.testing.assert_allclose(x, xr, rtol=1e-8, atol=1e-9)
+            _same_measure(w, x, wr, xr)
+    # batched + torch in/out
+    ms = torch.from_numpy(np.stack([g['quad/N4/rms'], g['quad/N4/rms']])).cuda()
+    w, x = moment_quadrature_nd(ms, gram_and_hankel_indices_graded_lexico(4, 2))
+    assert w.is_cuda and w.shape == (2, 100) and x.shape == (2, 100, 2) and torch.equal(w[0], w[1])
+    # ldl=True: the ordinary rule on a PD Gram matrix; with a negative pivot the eps-substituted factor puts nodes at
+    # ~1e16 and nothing below eps |K| ~ 1 is resolved by ANY eigen-solver -- the large nodes and finiteness are compared
+    s = np.load(os.path.join(GOLD, 'golden_stable.npz'))
+    for N in (2, 3):
+        inds = gram_and_hankel_indices_graded_lexico(N, 2)
+        w, x = moment_quadrature_nd(s[f'nd/N{N}/ms_pd'], inds, ldl=True)
+        (w, x), (wr, xr) = _canon(w, x), _canon(s[f'nd/N{N}/w_pd'], s[f'nd/N{N}/x_pd'])
+        np.testing.assert_allclose(x, xr, rtol=1e-8, atol=1e-9)
+        _same_measure(w, x, wr, xr)
+    w, x = moment_quadrature_nd(s['nd/N2/ms'], gram_and_hankel_indices_graded_lexico(2, 2), ldl=True)
+    (w, x), (wr, xr) = _canon(w, x), _canon(s['nd/N2/w'], s['nd/N2/x'])
+    np.testing.assert_allclose(x, xr, rtol=1e-8, atol=1e-9)
+    _same_measure(w, x, wr, xr)
+    w, x = moment_quadrature_nd(s['nd/N3/ms'], gram_and_hankel_indices_graded_lexico(3, 2), ldl=True)
+    assert np.isfinite(w).all() and np.isfinite(x).all()
+    np.testing.assert_allclose(np.abs(x).max(), np.abs(s['nd/N3/x']).max(), rtol=1e-6)
+    assert np.isnan(moment_quadrature_nd(s['nd/N3/ms'], gram_and_hankel_indices_graded_lexico(3, 2))[0]).all()
