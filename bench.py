@@ -275,8 +275,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         # rank 0 must print exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            del os.environ['NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -384,7 +384,8 @@ def main():
     e2e = None
     e2e_nell = None
     if not args.no_e2e:
-        Be = min(args.e2e_batch, B)
+        # pinned host buffers scale with the number of ranks on the node (16.8 GB of history per 131072 filters)
+        Be = min(max(16384, args.e2e_batch // world), B)
         ys_host = torch.empty((Be, T), dtype=torch.uint8).pin_memory()
         ys_host.copy_(ys[:Be])
         hist_bufs = {'ms': torch.empty((Be, T, M), dtype=torch.float64).pin_memory(),

@@ -15,6 +15,8 @@ T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 mode = sys.argv[4] if len(sys.argv) > 4 else 'raw'
 recompute = os.environ.get('MFS_RECOMPUTE', '0') == '1'
 history = sys.argv[5] if len(sys.argv) > 5 else 'full'
+seg = int(os.environ['MFS_SEG']) if 'MFS_SEG' in os.environ else None
+bufs = {}
 dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
 fam = sde_cond_moments_tme(drift, disp, dt, 3)
 ys = benes_bernoulli_ys_torch(B, T, 667, 'cuda')
@@ -22,7 +24,8 @@ for _ in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if mode == 'raw':
-        out = moment_filter_rms(fam[0], pmf, ic.rms, ys, history=history, return_status=True, recompute_predict_quadrature=recompute)
+        out = moment_filter_rms(fam[0], pmf, ic.rms, ys, history=history, return_status=True, recompute_predict_quadrature=recompute, segment_steps=seg, out=bufs)
+        bufs = {'ms': out[0], 'nell': out[1], 'status': out[2]} if history != 'none' else {'nell': out[1], 'status': out[2]}
     else:
         out = moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys, history=history, return_status=True, recompute_predict_quadrature=recompute)
     e1.record()
