@@ -320,9 +320,14 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
       for (int c = 0; c < S; ++c) Vr[c] = z[c];
     }
     unsigned neg = 1u << (S - 1);            // bit i <=> coupling e[i] negligible; bit S-1 is a sentinel
+    double bound = 0.0;                      // Gershgorin bound of the spectrum: every |d| of the iteration stays below it
 #pragma unroll
-    for (int i = 0; i + 1 < S; ++i)
+    for (int i = 0; i + 1 < S; ++i) {
       if (fabs(qe[i]) <= kEps * (fabs(qd[i]) + fabs(qd[i + 1]))) neg |= 1u << i;
+      bound = fmax(bound, fabs(qd[i]) + fabs(qe[i]) + (i > 0 ? fabs(qe[i - 1]) : 0.0));
+    }
+    bound = fmax(bound, fabs(qd[S - 1]) + (S > 1 ? fabs(qe[S - 2]) : 0.0));
+    const double tiny = 2.0 * kEps * bound;
     int l = 0, iter = 0;
     bool done = false, bad = false;
     for (;;) {
@@ -384,9 +389,12 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
             z[i + 1] = fma(sn, z[i], cs * z1);
             z[i] = fma(cs, z[i], -sn * z1);
           }
-          // e[i+1] and d[i+1], d[i+2] are final for this sweep: refresh the negligibility bit
-          const bool small = e_new <= kEps * (fabs(d_new) + fabs(d_below));
-          neg = small ? (neg | (1u << (i + 1))) : (neg & ~(1u << (i + 1)));
+          // e[i+1] and d[i+1], d[i+2] are final for this sweep.  Inside a block every bit is clear, so bits are only ever
+          // SET; `tiny` (2 eps x a bound of the spectrum) is a necessary condition that keeps the exact test off the
+          // common path.
+          if (e_new <= tiny) {
+            if (e_new <= kEps * (fabs(d_new) + fabs(d_below))) neg |= 1u << (i + 1);
+          }
           d_below = d_new;
         }
       };
@@ -408,8 +416,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
           const double dl = qd[l] - pp;
           qd[l] = dl;
           qe[l] = g;
-          const bool small = fabs(g) <= kEps * (fabs(dl) + fabs(qd[l + 1]));
-          neg = small ? (neg | (1u << l)) : (neg & ~(1u << l));
+          if (fabs(g) <= tiny && fabs(g) <= kEps * (fabs(dl) + fabs(qd[l + 1]))) neg |= 1u << l;
         }
       }
     }
