@@ -169,6 +169,16 @@ def secondary_legs(device_index, fp64_peak):
                                   f'history=last', 'kernel_ms': ms, 'nominal_flop_per_step': w_nd,
                         'fp64_frac_nominal': rate * w_nd / fp64_peak,
                         'diverged_frac': float((res[-1] >= 0).double().mean().item())}
+    # ---- the reference's data simulator (ss_models.py:49-54: 100 TME-3 Gaussian sub-steps per dt, T = 100) + Bernoulli
+    from mfs_b200.simulate import simulate_1d
+    from mfs_b200.one_dim.ss_models import benes_bernoulli
+    dtb, Tb, _, icb, driftb, dispb, _, pmfb, _ = benes_bernoulli(8)
+    Bs = 1000000
+    ms, _ = timed(lambda: simulate_1d(driftb, dispb, dtb, Tb, icb, pmfb, Bs, 1, device=dev))
+    out['simulator'] = {'metric': 'benes_bernoulli_simulated_trajectory_steps_per_s', 'value': Bs * Tb / (ms * 1e-3),
+                        'unit': 'trajectory-steps/s (each = 100 TME-3 Gaussian sub-steps + one Bernoulli draw)',
+                        'config': f'{Bs} trajectories x T={Tb}, 100 sub-steps, Philox4x32-10 + Box-Muller in the kernel',
+                        'kernel_ms': ms, 'sub_steps_per_s': Bs * Tb * 100 / (ms * 1e-3)}
     # ---- grid filter
     n, Bg, steps, Tg = 2000, 16384, 100, 1
     xs = np.linspace(-6., 6., n)
@@ -266,7 +276,7 @@ def main():
     from mfs_b200.one_dim.filtering import moment_filter_rms, moment_filter_cms
     from mfs_b200.one_dim.moments import sde_cond_moments_tme
     from mfs_b200.one_dim.ss_models import benes_bernoulli
-    from mfs_b200.synthetic import benes_bernoulli_ys_torch
+    from mfs_b200.simulate import simulate_1d
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -290,7 +300,9 @@ def main():
     fam = sde_cond_moments_tme(drift, disp, dt, 3)
 
     # the seeded synthetic workload of this rank's shard (weak scaling: B filters per GPU), resident in HBM
-    ys = benes_bernoulli_ys_torch(B, T, 666 + 1 + 1000 * rank, dev)
+    # (mfs_simulate_1d, exact Benes transition law; one Philox stream for the whole job: rank r owns trajectories
+    # [r B, (r + 1) B), so the N-GPU job filters the same records whatever N is)
+    ys = simulate_1d(drift, disp, dt, T, ic, pmf, B, 666 + 1, scheme='benes_exact', traj_offset=rank * B, device=dev)[2]
     out_bufs = {'nell': torch.empty(B, dtype=torch.float64, device=dev),
                 'status': torch.empty(B, dtype=torch.int32, device=dev)}
     if args.history == 'full':
@@ -461,7 +473,9 @@ def main():
                                    f'transition, N={N} nodes ({M} moments), T={T}, {B} independent filters per GPU',
                        'N': N, 'T': T, 'batch_per_gpu': B, 'global_batch': B * world, 'mode': args.mode,
                        'history': args.history, 'sharding': f'batch axis over {world} rank(s), no data-path collective',
-                       'l2': 'inputs_larger_than_l2 (ys 1 GB, outputs 128 GB per step)', 'seed': 667},
+                       'l2': 'inputs_larger_than_l2 (ys 1 GB, outputs 128 GB per step)', 'seed': 667,
+                       'data_source': 'simulated on the device by mfs_simulate_1d (exact Benes transition law, '
+                                      'Philox4x32-10 stream, trajectory ids sharded over ranks)'},
             'roofline': {'bound': 'fp64_fma', 'achieved': achieved_tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / (fp64_peak / 1e12), 'traffic': traffic,
                          'peak_source': 'measured live: mfs_fp64_peak DFMA micro-benchmark on this GPU '

@@ -253,6 +253,63 @@ int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, 
 int mfs_characteristic_fn_1d(int32_t N, int64_t B, int64_t m, const double* ms, const double* mean, const double* scale,
                              const double* zs, double* out, void* stream);
 
+/* ---- data simulators: the step before the filter ---------------------------------------------------------------------
+ * One trajectory per thread; random numbers from a counter-based Philox4x32-10 stream keyed by `seed` and indexed by
+ * (traj_offset + b, time step, draw), so a batch sharded over ranks (each passing its own traj_offset) equals the
+ * single-GPU batch.  The reference draws from jax.random keys (rng_keys.npy), which cannot be reproduced without JAX:
+ * the LAW of (x0, xs, ys) is the reference's, the stream is this library's (restated in oracle/mfs_oracle_sim.py). */
+enum {
+  MFS_SIM_TME = 0,         /* simulate_sde with tme.mean_and_cov(order) Gaussian sub-steps: mfs/utils.py:190-249,
+                              mfs/one_dim/ss_models.py:49-54, 86-91 (order 1 = Euler--Maruyama)                     */
+  MFS_SIM_BENES_EXACT = 1  /* exact Benes transition: N(x +- dt, dt) w.p. (1 +- tanh x)/2 (bench data; drift ignored) */
+};
+#define MFS_SIM_MAX_COMPONENTS 8
+
+typedef struct mfs_simulate1d_args {
+  int32_t abi_version;
+  int32_t scheme;             /* MFS_SIM_* */
+  int32_t tme_order;          /* 1..3 */
+  int32_t integration_steps;  /* sub-steps per dt (reference: 100) */
+  int32_t drift_id;           /* MFS_DRIFT_* */
+  int32_t meas_id;            /* MFS_MEAS_*: Bernoulli(logistic) / Poisson(softplus) / h x + r N(0,1) */
+  int32_t ys_dtype;           /* MFS_YS_* */
+  int32_t n_components;       /* initial Gaussian mixture, GaussianSum1D (mfs/utils.py:31-58) */
+  int64_t B, T;
+  double dt, dispersion;
+  const double* trans_params; int64_t trans_param_stride;   /* device [B|1][MFS_MAX_PARAMS] */
+  const double* meas_params;  int64_t meas_param_stride;    /* device [B|1][MFS_MAX_PARAMS] */
+  double init_means[MFS_SIM_MAX_COMPONENTS], init_variances[MFS_SIM_MAX_COMPONENTS], init_weights[MFS_SIM_MAX_COMPONENTS];
+  uint64_t seed;
+  uint64_t traj_offset;       /* global id of trajectory b = traj_offset + b */
+  void* ys_out;  int64_t ys_stride_b, ys_stride_t;          /* device, y[b][t]; may be NULL */
+  double* xs_out; int64_t xs_stride_b, xs_stride_t;         /* device, x[b][t] = state at t_{k+1}; may be NULL */
+  double* x0_out;                                           /* device [B]; may be NULL */
+} mfs_simulate1d_args;
+
+/* Enqueue B trajectories x T steps.  Replaces init_cond.sampler + simulate_trajectory + jax.random.bernoulli/poisson
+ * per Monte-Carlo run (dardel/benes_bernoulli/mf.py:73-80, dardel/parameter_estimation/mf.py:58-65). */
+int mfs_simulate_1d(const mfs_simulate1d_args* a, void* stream);
+
+typedef struct mfs_simulate_lv_args {
+  int32_t abi_version;
+  int32_t integration_steps;  /* Milstein sub-steps per dt (reference: 100) */
+  int32_t n_components;
+  int32_t obs_dim;            /* measured coordinate (prey--predator: 0) */
+  int64_t B, T;
+  double dt;
+  const double* trans_params; int64_t trans_param_stride;   /* device [B|1][8]: alpha, beta, delta, gamma, sigma */
+  const double* meas_params;  int64_t meas_param_stride;    /* device [B|1][4]: c0, c1 of the logistic-cubic emission */
+  double init_means[MFS_SIM_MAX_COMPONENTS][2], init_covs[MFS_SIM_MAX_COMPONENTS][4], init_weights[MFS_SIM_MAX_COMPONENTS];
+  uint64_t seed, traj_offset;
+  uint8_t* ys_out;            /* device [B][T]; may be NULL */
+  double* xs_out;             /* device [B][T][2]; may be NULL */
+  double* x0_out;             /* device [B][2]; may be NULL */
+} mfs_simulate_lv_args;
+
+/* Lotka--Volterra Milstein simulator + Bernoulli measurements: prey_predator(...).simulate,
+ * mfs/multi_dims/ss_models.py:76-93. */
+int mfs_simulate_lv(const mfs_simulate_lv_args* a, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process since load (all threads). */
 int64_t mfs_launch_count(void);
 

@@ -82,10 +82,46 @@ class BruteForceArgs(ctypes.Structure):
 
 
 BF_METHOD = {'chapman-euler': 0, 'chapman-tme': 1, 'kolmogorov': 2}
+SIM_SCHEME = {'tme': 0, 'benes_exact': 1}
+SIM_MAX_COMPONENTS = 8
+
+
+class Simulate1dArgs(ctypes.Structure):
+    """Mirror of ``mfs_simulate1d_args``."""
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('scheme', ctypes.c_int32), ('tme_order', ctypes.c_int32),
+        ('integration_steps', ctypes.c_int32), ('drift_id', ctypes.c_int32), ('meas_id', ctypes.c_int32),
+        ('ys_dtype', ctypes.c_int32), ('n_components', ctypes.c_int32),
+        ('B', ctypes.c_int64), ('T', ctypes.c_int64), ('dt', ctypes.c_double), ('dispersion', ctypes.c_double),
+        ('trans_params', ctypes.c_void_p), ('trans_param_stride', ctypes.c_int64),
+        ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
+        ('init_means', ctypes.c_double * SIM_MAX_COMPONENTS), ('init_variances', ctypes.c_double * SIM_MAX_COMPONENTS),
+        ('init_weights', ctypes.c_double * SIM_MAX_COMPONENTS),
+        ('seed', ctypes.c_uint64), ('traj_offset', ctypes.c_uint64),
+        ('ys_out', ctypes.c_void_p), ('ys_stride_b', ctypes.c_int64), ('ys_stride_t', ctypes.c_int64),
+        ('xs_out', ctypes.c_void_p), ('xs_stride_b', ctypes.c_int64), ('xs_stride_t', ctypes.c_int64),
+        ('x0_out', ctypes.c_void_p),
+    ]
+
+
+class SimulateLvArgs(ctypes.Structure):
+    """Mirror of ``mfs_simulate_lv_args``."""
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('integration_steps', ctypes.c_int32), ('n_components', ctypes.c_int32),
+        ('obs_dim', ctypes.c_int32), ('B', ctypes.c_int64), ('T', ctypes.c_int64), ('dt', ctypes.c_double),
+        ('trans_params', ctypes.c_void_p), ('trans_param_stride', ctypes.c_int64),
+        ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
+        ('init_means', (ctypes.c_double * 2) * SIM_MAX_COMPONENTS), ('init_covs', (ctypes.c_double * 4) * SIM_MAX_COMPONENTS),
+        ('init_weights', ctypes.c_double * SIM_MAX_COMPONENTS),
+        ('seed', ctypes.c_uint64), ('traj_offset', ctypes.c_uint64),
+        ('ys_out', ctypes.c_void_p), ('xs_out', ctypes.c_void_p), ('x0_out', ctypes.c_void_p),
+    ]
+
 
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
-           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd')
+           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd',
+           'mfs_simulate_1d', 'mfs_simulate_lv')
 
 _lib = None
 _lock = threading.Lock()
@@ -148,6 +184,10 @@ def lib() -> ctypes.CDLL:
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.mfs_moment_quadrature_nd.restype = ctypes.c_int
+        L.mfs_simulate_1d.argtypes = [ctypes.POINTER(Simulate1dArgs), ctypes.c_void_p]
+        L.mfs_simulate_1d.restype = ctypes.c_int
+        L.mfs_simulate_lv.argtypes = [ctypes.POINTER(SimulateLvArgs), ctypes.c_void_p]
+        L.mfs_simulate_lv.restype = ctypes.c_int
         L.mfs_launch_count.restype = ctypes.c_int64
         L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]
