@@ -225,6 +225,18 @@ int mfs_functor_lookup(const char* kind, const char* name, int32_t* id);
  * Replaces: jax.jit(moment_filter_{rms,cms,scms})(ys) per trajectory (dardel/benes_bernoulli/mf.py:51-67). */
 int mfs_filter_1d(const mfs_filter1d_args* a, void* stream);
 
+/* nell AND its gradient w.r.t. functor parameters in one pass (forward-mode derivative carried through the scan).
+ * Replaces jax.value_and_grad of the objective the reference hands to L-BFGS-B
+ * (dardel/parameter_estimation/mf.py:37-73; "differentiable in the parameter", README.md:45).
+ * `a` as for mfs_filter_1d (RAW or CENTRAL mode; ms_out / mean_out are not written: out_mode must be MFS_OUT_NONE;
+ * `stable` must be 0).  tangent_ids[k] in [0, MFS_MAX_PARAMS) selects trans_params[id], in [MFS_MAX_PARAMS,
+ * 2 MFS_MAX_PARAMS) selects meas_params[id - MFS_MAX_PARAMS].  Writes nell_out[b], status_out[b] and
+ * grad_out[b][MFS_GRAD_MAX_TANGENTS] (row stride MFS_GRAD_MAX_TANGENTS; slots >= n_tangents are 0); a failed filter
+ * gives NaN value and gradient.  Device pointers (tangent_ids is a HOST array). */
+#define MFS_GRAD_MAX_TANGENTS 2
+int mfs_filter_1d_grad(const mfs_filter1d_args* a, int32_t n_tangents, const int32_t* tangent_ids, double* grad_out,
+                       void* stream);
+
 /* Same contract with HOST pointers everywhere (ys, ms0, params, outputs).  The batch is cut into chunks that are
  * pipelined H2D -> kernel -> D2H on `device` (double-buffered, two streams); returns after the last D2H completed.
  * `chunk_filters` = 0 picks a default. */

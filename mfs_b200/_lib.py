@@ -22,6 +22,7 @@ MEAS = {'bernoulli_logistic_cubic': 0, 'poisson_softplus': 1, 'gaussian': 2}
 YS_DTYPE = {'uint8': 0, 'bool': 0, 'int32': 1, 'float64': 2}
 OUT_MODE = {'full': 0, 'last': 1, 'none': 2}
 FLAG_RECOMPUTE_PREDICT_QUADRATURE = 1
+GRAD_MAX_TANGENTS = 2
 
 
 class Filter1dArgs(ctypes.Structure):
@@ -121,7 +122,7 @@ class SimulateLvArgs(ctypes.Structure):
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
            'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd',
-           'mfs_simulate_1d', 'mfs_simulate_lv')
+           'mfs_simulate_1d', 'mfs_simulate_lv', 'mfs_filter_1d_grad')
 
 _lib = None
 _lock = threading.Lock()
@@ -161,6 +162,9 @@ def lib() -> ctypes.CDLL:
         L.mfs_functor_lookup.restype = ctypes.c_int
         L.mfs_filter_1d.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_void_p]
         L.mfs_filter_1d.restype = ctypes.c_int
+        L.mfs_filter_1d_grad.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                         ctypes.c_void_p, ctypes.c_void_p]
+        L.mfs_filter_1d_grad.restype = ctypes.c_int
         L.mfs_filter_1d_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int64]
         L.mfs_filter_1d_workspace_bytes.restype = ctypes.c_int64
         L.mfs_filter_1d_host.argtypes = [ctypes.POINTER(Filter1dArgs), ctypes.c_int, ctypes.c_int64]

@@ -122,6 +122,10 @@ static cudaError_t dispatch(const mfs_filter1d_args& a, const SegInfo& g, cudaSt
   }
 }
 
+// nell + gradient (filter1d_grad.cuh), one translation unit per N
+template <int N>
+cudaError_t launch_filter1d_grad(const mfs_filter1d_args& a, const GradInfo& g, cudaStream_t stream);
+
 // NaN tails of the filters that failed (JAX semantics: everything after a failed Cholesky is NaN until the end of the
 // scan).  Written here, one warp per failed filter with coalesced stores, instead of by the failing thread itself --
 // which would hold its whole warp for up to T - t serial store rounds.
@@ -350,6 +354,36 @@ int64_t mfs_filter_1d_workspace_bytes(int32_t N, int64_t B, int64_t T) {
 int mfs_filter_1d(const mfs_filter1d_args* a, void* stream) {
   if (int rc = validate(a)) return rc;
   return launch_device(*a, static_cast<cudaStream_t>(stream));
+}
+
+int mfs_filter_1d_grad(const mfs_filter1d_args* a, int32_t n_tangents, const int32_t* tangent_ids, double* grad_out,
+                       void* stream) {
+  if (int rc = validate(a)) return rc;
+  if (a->mode == MFS_MODE_SCALED) return fail("mfs_filter_1d_grad: raw and central moments only");
+  if (a->stable) return fail("mfs_filter_1d_grad: stable=True is not differentiable (eps-substituted pivots); not offered");
+  if (n_tangents < 1 || n_tangents > MFS_GRAD_MAX_TANGENTS) return fail("mfs_filter_1d_grad: n_tangents=%d outside [1, %d]", n_tangents, MFS_GRAD_MAX_TANGENTS);
+  if (!tangent_ids || !grad_out) return fail("mfs_filter_1d_grad: tangent_ids / grad_out must not be NULL");
+  GradInfo g = {};
+  for (int k = 0; k < 4; ++k) g.tangent_ids[k] = -1;
+  for (int k = 0; k < n_tangents; ++k) {
+    if (tangent_ids[k] < 0 || tangent_ids[k] >= 2 * MFS_MAX_PARAMS) return fail("mfs_filter_1d_grad: tangent id %d outside [0, %d)", tangent_ids[k], 2 * MFS_MAX_PARAMS);
+    g.tangent_ids[k] = tangent_ids[k];
+  }
+  g.grad_out = grad_out;
+  g.n_slots = MFS_GRAD_MAX_TANGENTS;
+  if (a->B == 0) return 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a->N) {
+#define MFS_CASE(n) case n: e = launch_filter1d_grad<n>(*a, g, s); break;
+    MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
+    MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
+#undef MFS_CASE
+    default: break;
+  }
+  if (e != cudaSuccess) return fail("mfs_filter_1d_grad: kernel launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_filters) {

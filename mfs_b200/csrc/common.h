@@ -10,4 +10,11 @@ int fail(const char* fmt, ...);
 // Adds n to the process-wide kernel-launch counter (mfs_launch_count).
 void count_launches(int64_t n);
 
+// Tangent selection of the gradient kernel (filter1d_grad.cuh), filled in by mfs_filter_1d_grad.
+struct GradInfo {
+  int32_t tangent_ids[4];  // per tangent slot: 0..3 -> trans_params[i], 4..7 -> meas_params[i - 4], -1 -> unused
+  double* grad_out;        // [B][n_slots]
+  int32_t n_slots;
+};
+
 }  // namespace mfs

@@ -51,10 +51,13 @@ def _ys_dtype_code(dtype_name: str) -> int:
 
 def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stable: bool, history: str,
          device: Optional[int], return_status: bool, chunk_filters: int, out: Optional[dict] = None,
-         recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None):
+         recompute_predict_quadrature: bool = False, segment_steps: Optional[int] = None,
+         grad_ids: Optional[list] = None):
     if history not in _lib.OUT_MODE:
         raise ValueError(f"history must be one of {sorted(_lib.OUT_MODE)}")
     on_device = _is_torch_cuda(ys)
+    if grad_ids is not None and not on_device:
+        raise ValueError('value_and_grad takes ys as a CUDA tensor (device path only)')
     if not on_device and type(ys).__module__.startswith('torch'):
         ys = ys.numpy()
     if not on_device:
@@ -170,9 +173,22 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             keep.append(ws)
             a.segment_steps, a.workspace, a.workspace_bytes = seg, ws.data_ptr(), ws_bytes
+        grad = None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(L.mfs_filter_1d(ctypes.byref(a), ctypes.c_void_p(stream)))
+            if grad_ids is None:
+                _lib.check(L.mfs_filter_1d(ctypes.byref(a), ctypes.c_void_p(stream)))
+            else:
+                # forward-mode nell + gradient kernel, MFS_GRAD_MAX_TANGENTS parameters per pass
+                W = _lib.GRAD_MAX_TANGENTS
+                grad = torch.zeros((B, len(grad_ids)), **f64)
+                for k0 in range(0, len(grad_ids), W):
+                    ids = list(grad_ids[k0:k0 + W])
+                    g = torch.empty((B, W), **f64)
+                    keep.append(g)
+                    _lib.check(L.mfs_filter_1d_grad(ctypes.byref(a), len(ids), (ctypes.c_int32 * len(ids))(*ids),
+                                                    ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(stream)))
+                    grad[:, k0:k0 + len(ids)] = g[:, :len(ids)]
         for t in keep:   # inputs must outlive the asynchronous kernel
             t.record_stream(torch.cuda.current_stream(dev))
         reshape = lambda t, tail: None if t is None else t.reshape(batch_shape + tail)
@@ -233,6 +249,8 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
         'nell': reshape(nell, ()),
         'status': reshape(status, ()),
     }
+    if grad_ids is not None:
+        out['grad'] = grad.reshape(batch_shape + (len(grad_ids),))
     return out
 
 
