@@ -176,3 +176,24 @@ def test_argument_errors():
         moment_filter_rms_value_and_grad(fam[0], pmf(3.), ic.rms, ys.cpu().numpy())
     with pytest.raises(TypeError):
         moment_filter_rms_value_and_grad(np.tanh, pmf(3.), ic.rms, ys)
+
+
+def test_batched_estimation_recovers_the_parameters():
+    """dardel/parameter_estimation/mf.py in miniature: records simulated at theta = (3, 3), fits started at (0.1, 0.1)
+    like the reference; the batched BFGS ends at stationary points and the estimates scatter around the truth."""
+    from mfs_b200.simulate import simulate_1d
+    from mfs_b200.one_dim.estimation import estimate_well_poisson
+    N, T, B = 5, 1000, 48
+    dt, _, _, ic, drift, disp, _, pmf, _ = well_poisson(3., N)
+    _, _, ys = simulate_1d(drift(3.), disp, dt, T, ic, pmf(3.), B, 77, integration_steps=20)
+    theta, res = estimate_well_poisson(ys, N)
+    ok = res.success
+    assert float(ok.double().mean()) > 0.9
+    th = theta[ok]
+    assert abs(float(th[:, 0].median()) - 3.) < 0.8 and abs(float(th[:, 1].median()) - 3.) < 0.5
+    # stationarity in the reference's unconstrained variables
+    assert float(res.grad[ok].abs().amax(1).median()) < 1e-3
+    # the fit improves on the starting point for every run
+    fam = sde_cond_moments_tme_normal(drift(0.1), disp, dt, 2, N)
+    nell0 = moment_filter_cms(fam[1], fam[3], pmf(0.1), ic.cms, ic.mean, ys, history='none')[2]
+    assert bool((res.fun[ok] < nell0[ok]).all())
