@@ -269,7 +269,7 @@ int mfs_characteristic_fn_1d(int32_t N, int64_t B, int64_t m, const double* ms, 
  * One trajectory per thread; random numbers from a counter-based Philox4x32-10 stream keyed by `seed` and indexed by
  * (traj_offset + b, time step, draw), so a batch sharded over ranks (each passing its own traj_offset) equals the
  * single-GPU batch.  The reference draws from jax.random keys (rng_keys.npy), which cannot be reproduced without JAX:
- * the LAW of (x0, xs, ys) is the reference's, the stream is this library's (restated in oracle/mfs_oracle_sim.py). */
+ * the LAW of (x0, xs, ys) is the reference's, the stream is this library's. */
 enum {
   MFS_SIM_TME = 0,         /* simulate_sde with tme.mean_and_cov(order) Gaussian sub-steps: mfs/utils.py:190-249,
                               mfs/one_dim/ss_models.py:49-54, 86-91 (order 1 = Euler--Maruyama)                     */

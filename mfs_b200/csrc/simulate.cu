@@ -14,7 +14,7 @@
 // reproduced without JAX, so the simulators define their own counter-based stream: Philox4x32-10 (Salmon et al. 2011),
 // key = the 64-bit seed, counter = (trajectory id lo, trajectory id hi, time index, draw index).  A trajectory's
 // numbers depend only on (seed, global trajectory id), so a batch sharded over ranks with `traj_offset` equals the
-// single-GPU batch bit for bit, and the CPU oracle (oracle/mfs_oracle_sim.py) regenerates the same stream.
+// single-GPU batch bit for bit, and the stream can be regenerated on the host from (seed, trajectory id) alone.
 //   time index 0: initial condition (draw 0: mixture component, draw 1: normals); time index t+1: step t;
 //   draw j < 2^31: sub-step normals (1-D: sub-steps 2j, 2j+1; 2-D: sub-step j, one normal per dimension);
 //   draw 0x80000000: the measurement; draw 0x80000001: the sign of the exact Benes transition.

@@ -127,3 +127,20 @@ def test_no_product_import_of_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h', 'Makefile')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in txt.lower().replace('no oracle', ''), os.path.join(dirpath, f)
+
+
+def test_reference_result_files(tmp_path):
+    """dardel/benes_bernoulli/mf.py:83-92 and dardel/parameter_estimation/mf.py:76-77: file names and keys."""
+    from mfs_b200.results import save_benes_bernoulli_mf, save_parameter_estimation_mf
+    rng = np.random.default_rng(0)
+    cmss, means, nell = rng.normal(size=(3, 7, 4)), rng.normal(size=(3, 7)), rng.normal(size=3)
+    names = save_benes_bernoulli_mf(tmp_path, 'central', 2, (cmss, means, nell), transition='tme_3', first_mc=10)
+    assert [os.path.basename(n) for n in names] == [f'central_tme_3_N_2_mc_{k}.npz' for k in (10, 11, 12)]
+    f = np.load(names[1])
+    assert sorted(f.files) == ['cmss', 'means', 'nell']
+    assert np.array_equal(f['cmss'], cmss[1]) and np.array_equal(f['means'], means[1]) and f['nell'] == nell[1]
+    names = save_benes_bernoulli_mf(tmp_path, 'raw', 3, (cmss, nell))
+    assert os.path.basename(names[0]) == 'raw_N_3_mc_0.npz' and sorted(np.load(names[0]).files) == ['nell', 'rmss']
+    names = save_parameter_estimation_mf(tmp_path, 7, rng.normal(size=(2, 2)), np.array([True, False]), euler=True)
+    f = np.load(names[1])
+    assert os.path.basename(names[1]) == 'N_7_euler_mc_1.npz' and not bool(f['success']) and f['opt_params'].shape == (2,)
