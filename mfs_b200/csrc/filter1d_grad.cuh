@@ -66,7 +66,7 @@ template <int P> MFS_DEV Dual<P> operator*(const Dual<P>& a, const Dual<P>& b) {
 }
 template <int P> MFS_DEV Dual<P> operator/(const Dual<P>& a, const Dual<P>& b) {
   Dual<P> r;
-  const double inv = 1.0 / b.v;
+  const double inv = rcp_fast(b.v);     // <= 2 ulp, no denormal / inf branches (quadrature.cuh)
   r.v = a.v * inv;
 #pragma unroll
   for (int k = 0; k < P; ++k) r.d[k] = fma(-r.v, b.d[k], a.d[k]) * inv;
@@ -83,7 +83,7 @@ template <int P> MFS_DEV Dual<P> operator*(const Dual<P>& a, double b) {
   return r;
 }
 template <int P> MFS_DEV Dual<P> operator*(double b, const Dual<P>& a) { return a * b; }
-template <int P> MFS_DEV Dual<P> operator/(const Dual<P>& a, double b) { return a * (1.0 / b); }
+template <int P> MFS_DEV Dual<P> operator/(const Dual<P>& a, double b) { return a * rcp_fast(b); }
 template <int P> MFS_DEV Dual<P> operator/(double a, const Dual<P>& b) { return make_dual<P>(a) / b; }
 
 // f(a) with derivative df: chain rule
@@ -97,9 +97,9 @@ MFS_DEV double t_sqrt(double a) { return sqrt(a); }
 MFS_DEV double t_exp(double a) { return exp(a); }
 MFS_DEV double t_log(double a) { return log(a); }
 MFS_DEV double t_tanh(double a) { return tanh(a); }
-template <int P> MFS_DEV Dual<P> t_sqrt(const Dual<P>& a) { const double s = sqrt(a.v); return chain(a, s, 0.5 / s); }
+template <int P> MFS_DEV Dual<P> t_sqrt(const Dual<P>& a) { const double r = rsqrt_fast(a.v); return chain(a, a.v * r, 0.5 * r); }
 template <int P> MFS_DEV Dual<P> t_exp(const Dual<P>& a) { const double e = exp(a.v); return chain(a, e, e); }
-template <int P> MFS_DEV Dual<P> t_log(const Dual<P>& a) { return chain(a, log(a.v), 1.0 / a.v); }
+template <int P> MFS_DEV Dual<P> t_log(const Dual<P>& a) { return chain(a, log(a.v), rcp_fast(a.v)); }
 template <int P> MFS_DEV Dual<P> t_tanh(const Dual<P>& a) { const double t = tanh(a.v); return chain(a, t, fma(-t, t, 1.0)); }
 
 template <class S> struct Scalar;
@@ -348,20 +348,29 @@ MFS_DEV S measurement_pdf_t(int meas_id, double y, double lgam, const S& x, cons
 // ---------------------------------------------------------------------------------------------------------------------
 template <class S, int N>
 MFS_DEV bool quadrature_t(const S (&ms)[2 * N], const S& mean, S (&w)[N], S (&x)[N]) {
-  S d[N], e[N];
+  S d[N], e[N], z[N];   // registers (compile-time indices); w / x are the caller's atom arrays (local memory)
   bool ok = jacobi_from_moments_t<S, N>(ms, d, e);
   if (!ok) return false;
-  ok = tridiag_ql_t<S, N>(d, e, w);
+  ok = tridiag_ql_t<S, N>(d, e, z);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    w[i] = w[i] * w[i];
+    w[i] = z[i] * z[i];
     x[i] = d[i] + mean;
   }
   return ok;
 }
 
+#ifndef MFS_GRAD_MIN_BLOCKS
+#define MFS_GRAD_MIN_BLOCKS 4
+#endif
+#ifdef MFS_GRAD_UNROLL_NODES
+#define MFS_NODE_LOOP _Pragma("unroll")
+#else
+#define MFS_NODE_LOOP _Pragma("unroll 1")
+#endif
+
 template <int N, int P>
-__global__ void __launch_bounds__(64) filter1d_grad_kernel(const mfs_filter1d_args A, const GradInfo G) {
+__global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(const mfs_filter1d_args A, const GradInfo G) {
   using S = Dual<P>;
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
@@ -394,22 +403,28 @@ __global__ void __launch_bounds__(64) filter1d_grad_kernel(const mfs_filter1d_ar
   for (int64_t t = 0; t < A.T && ok; ++t) {
     const double y = load_y(A.ys, A.ys_dtype, b * A.ys_stride_b + t * A.ys_stride_t);
     // ---- prediction (filtering.py:78-79 / :145-148)
+    // The loops over the N atoms are ROLLED (MFS_NODE_LOOP): w, x, mu, var, g are indexed dynamically and live in
+    // local memory, the 2N moment accumulators stay in registers.  Unrolled, a step is ~24k straight-line instructions
+    // (385 KB at N = 7) and the kernel stalls on instruction fetch (ncu v1: stall_no_instruction 3.1 per issue).
     S mu[N], var[N];
     S g[N][7];
     if (normal_family) {
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) normal_mean_var_t<S>(A.trans_id, A.drift_id, A.tme_order, x[i], c, dt, tprm, mu[i], var[i]);
     } else {
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) {
         const JetT<S> j = drift_jet_t<S>(A.drift_id, x[i], tprm);
-        tme_coefficients_t<S>(j, c, dt, A.tme_order, g[i]);
-        mu[i] = x[i] + g[i][1];      // tme.expectation(identity) = x + sum_r dt^r/r! A^r x
+        S gi[7];
+        tme_coefficients_t<S>(j, c, dt, A.tme_order, gi);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g[i][k] = gi[k];
+        mu[i] = x[i] + gi[1];      // tme.expectation(identity) = x + sum_r dt^r/r! A^r x
       }
     }
     if (central) {
       S acc = make_dual<P>(0.0);
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) acc = acc + w[i] * mu[i];
       mean = acc;
     }
@@ -417,26 +432,31 @@ __global__ void __launch_bounds__(64) filter1d_grad_kernel(const mfs_filter1d_ar
     for (int p = 0; p < 2 * N; ++p) ms[p] = make_dual<P>(0.0);
     if (normal_family) {
       // moments of N(mu - mean, var): M_p = mu M_{p-1} + (p - 1) var M_{p-2}   (= the binomial sum of moments.py:70-74)
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) {
+        const S wi = w[i], vi = var[i];
         S m = central ? mu[i] - mean : mu[i];
-        if (val(var[i]) < 0.0) m.v = nan("");
+        if (val(vi) < 0.0) m.v = nan("");
         S m2 = make_dual<P>(1.0), m1 = m;
-        ms[0] = ms[0] + w[i];
-        ms[1] = ms[1] + w[i] * m1;
+        ms[0] = ms[0] + wi;
+        ms[1] = ms[1] + wi * m1;
 #pragma unroll
         for (int p = 2; p < 2 * N; ++p) {
-          const S mp = m * m1 + ((double)(p - 1) * var[i]) * m2;
-          ms[p] = ms[p] + w[i] * mp;
+          const S mp = m * m1 + ((double)(p - 1) * vi) * m2;
+          ms[p] = ms[p] + wi * mp;
           m2 = m1;
           m1 = mp;
         }
       }
     } else {
       // T_p(x) = p! sum_k g_k(x) delta^(p-k)/(p-k)!,  delta = x - mean (central) or x (raw)      moments.py:141-179
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) {
+        const S wi = w[i];
         const S delta = central ? x[i] - mean : x[i];
+        S gi[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) gi[k] = g[i][k];
         S pq[2 * N];
         pq[0] = make_dual<P>(1.0);
 #pragma unroll
@@ -446,8 +466,8 @@ __global__ void __launch_bounds__(64) filter1d_grad_kernel(const mfs_filter1d_ar
           S acc = make_dual<P>(0.0);
 #pragma unroll
           for (int k = 0; k < 7; ++k)
-            if (k <= p) acc = acc + g[i][k] * pq[p - k];
-          ms[p] = ms[p] + w[i] * acc;
+            if (k <= p) acc = acc + gi[k] * pq[p - k];
+          ms[p] = ms[p] + wi * acc;
         }
       }
       double f = 1.0;
@@ -459,25 +479,29 @@ __global__ void __launch_bounds__(64) filter1d_grad_kernel(const mfs_filter1d_ar
     if (!ok) { status = (int32_t)t; break; }
     const double lgam = (A.meas_id == MFS_MEAS_POISSON_SOFTPLUS) ? lgamma(y + 1.0) : 0.0;
     S cc = make_dual<P>(0.0);
-#pragma unroll
+    MFS_NODE_LOOP
     for (int i = 0; i < N; ++i) {
-      w[i] = w[i] * measurement_pdf_t<S>(A.meas_id, y, lgam, x[i], mprm);
-      cc = cc + w[i];
+      const S u = w[i] * measurement_pdf_t<S>(A.meas_id, y, lgam, x[i], mprm);
+      w[i] = u;
+      cc = cc + u;
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) w[i] = w[i] / cc;
+    {
+      const S cinv = 1.0 / cc;
+      MFS_NODE_LOOP
+      for (int i = 0; i < N; ++i) w[i] = w[i] * cinv;
+    }
     nell = nell - t_log(cc);
     // posterior moments (values only): the pivots the next prediction's Cholesky would see
     {
       double pm[2 * N], pa[N], pb[N];
       double pmean = 0.0;
       if (central) {
-#pragma unroll
+        MFS_NODE_LOOP
         for (int i = 0; i < N; ++i) pmean = fma(w[i].v, x[i].v, pmean);
       }
 #pragma unroll
       for (int p = 0; p < 2 * N; ++p) pm[p] = 0.0;
-#pragma unroll
+      MFS_NODE_LOOP
       for (int i = 0; i < N; ++i) {
         const double delta = x[i].v - pmean;
         double pw = w[i].v;
