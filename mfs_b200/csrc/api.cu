@@ -362,7 +362,9 @@ int mfs_filter_1d_grad(const mfs_filter1d_args* a, int32_t n_tangents, const int
   if (a->mode == MFS_MODE_SCALED) return fail("mfs_filter_1d_grad: raw and central moments only");
   if (a->stable) return fail("mfs_filter_1d_grad: stable=True is not differentiable (eps-substituted pivots); not offered");
   if (n_tangents < 1 || n_tangents > MFS_GRAD_MAX_TANGENTS) return fail("mfs_filter_1d_grad: n_tangents=%d outside [1, %d]", n_tangents, MFS_GRAD_MAX_TANGENTS);
-  if (!tangent_ids || !grad_out) return fail("mfs_filter_1d_grad: tangent_ids / grad_out must not be NULL");
+  if (!tangent_ids) return fail("mfs_filter_1d_grad: tangent_ids must not be NULL");
+  if (a->B == 0) return 0;
+  if (!grad_out) return fail("mfs_filter_1d_grad: grad_out must not be NULL");
   GradInfo g = {};
   for (int k = 0; k < 4; ++k) g.tangent_ids[k] = -1;
   for (int k = 0; k < n_tangents; ++k) {

@@ -263,8 +263,9 @@ int mfs_simulate_1d(const mfs_simulate1d_args* a, void* stream) {
   if (a->meas_id == MFS_MEAS_POISSON_SOFTPLUS && a->ys_out && a->ys_dtype == MFS_YS_U8) return fail("mfs_simulate_1d: Poisson counts need int32 or float64 ys");
   if (a->n_components < 1 || a->n_components > MFS_SIM_MAX_COMPONENTS) return fail("mfs_simulate_1d: n_components must be 1..%d", MFS_SIM_MAX_COMPONENTS);
   if (!(a->dt > 0.0)) return fail("mfs_simulate_1d: dt must be positive");
+  if (a->B == 0) return 0;
   if (!a->ys_out && !a->xs_out && !a->x0_out) return fail("mfs_simulate_1d: no output requested");
-  if (a->B == 0 || (a->T == 0 && !a->x0_out)) return 0;
+  if (a->T == 0 && !a->x0_out) return 0;
   const unsigned grid = (unsigned)((a->B + 127) / 128);
   simulate1d_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
   const cudaError_t e = cudaGetLastError();
@@ -283,8 +284,9 @@ int mfs_simulate_lv(const mfs_simulate_lv_args* a, void* stream) {
   if (a->obs_dim < 0 || a->obs_dim > 1) return fail("mfs_simulate_lv: obs_dim must be 0 or 1");
   if (!a->trans_params || !a->meas_params) return fail("mfs_simulate_lv: null parameter pointer");
   if (!(a->dt > 0.0)) return fail("mfs_simulate_lv: dt must be positive");
+  if (a->B == 0) return 0;
   if (!a->ys_out && !a->xs_out && !a->x0_out) return fail("mfs_simulate_lv: no output requested");
-  if (a->B == 0 || (a->T == 0 && !a->x0_out)) return 0;
+  if (a->T == 0 && !a->x0_out) return 0;
   const unsigned grid = (unsigned)((a->B + 127) / 128);
   simulate_lv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
   const cudaError_t e = cudaGetLastError();

@@ -197,3 +197,26 @@ def test_batched_estimation_recovers_the_parameters():
     fam = sde_cond_moments_tme_normal(drift(0.1), disp, dt, 2, N)
     nell0 = moment_filter_cms(fam[1], fam[3], pmf(0.1), ic.cms, ic.mean, ys, history='none')[2]
     assert bool((res.fun[ok] < nell0[ok]).all())
+
+
+def test_edge_shapes():
+    """Unbatched record (T,) -> scalars like the reference's obj_func; T = 1; empty batch; non-PD start -> NaN."""
+    N = 4
+    dt, _, ts, ic, drift, disp, emission, pmf, _ = well_poisson(3., N)
+    ys = synthetic.well_poisson_ys_numpy(3, 40, 675)
+    fam = sde_cond_moments_tme_normal(drift(2.5), disp, dt, 2, N)
+    nell, grad = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), ic.cms, ic.mean, dev(ys[0]))
+    assert nell.shape == () and grad.shape == (2,)
+    nb, gb = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), ic.cms, ic.mean, dev(ys))
+    assert torch.equal(nb[0], nell) and torch.equal(gb[0], grad)
+    n1, g1 = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), ic.cms, ic.mean, dev(ys[:, :1]))
+    v1 = moment_filter_cms(fam[1], fam[3], pmf(3.), ic.cms, ic.mean, dev(ys[:, :1]), history='none')[2]
+    np.testing.assert_allclose(n1.cpu().numpy(), v1.cpu().numpy(), rtol=1e-12)
+    assert bool(torch.isfinite(g1).all())
+    n0, g0 = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), ic.cms, ic.mean,
+                                              torch.empty((0, 7), dtype=torch.int32, device='cuda'))
+    assert n0.shape == (0,) and g0.shape == (0, 2)
+    bad = ic.cms.copy()
+    bad[2] = -1e-3
+    nbad, gbad, sbad = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), bad, ic.mean, dev(ys), return_status=True)
+    assert bool(torch.isnan(nbad).all()) and bool(torch.isnan(gbad).all()) and bool((sbad == 0).all())

@@ -141,3 +141,18 @@ def test_argument_errors():
         simulate_1d(np.tanh, disp, dt, T, ic, pmf, 8, 1)
     with pytest.raises(ValueError):
         simulate_1d(drift, disp, dt, T, ic, pmf, 8, 1, device='cpu')
+
+
+def test_edge_shapes():
+    dt, T, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(5)
+    x0, xs, ys = simulate_1d(drift, disp, dt, 5, ic, pmf, 0, 1, return_xs=True)
+    assert x0.shape == (0,) and xs.shape == (0, 5) and ys.shape == (0, 5)
+    x0, xs, ys = simulate_1d(drift, disp, dt, 0, ic, pmf, 9, 1, return_xs=True)
+    assert x0.shape == (9,) and ys.shape == (9, 0) and bool(torch.isfinite(x0).all())
+    ref = S.simulate_1d('benes', (), 1., dt, 0, *IC, 'bernoulli_logistic_cubic', (5., 0.), 9, 1)
+    assert np.max(np.abs(x0.cpu().numpy() - ref[0])) < 1e-13
+    # T not a multiple of 8 and an unaligned row pitch: the packed uint8 writer falls back to byte stores
+    for T_ in (1, 7, 9, 15):
+        _, _, y1 = simulate_1d(drift, disp, dt, T_, ic, pmf, 33, 2, scheme='benes_exact')
+        r = S.simulate_1d('benes', (), 1., dt, T_, *IC, 'bernoulli_logistic_cubic', (5., 0.), 33, 2, scheme='benes_exact')
+        assert np.array_equal(y1.cpu().numpy().astype(np.float64), r[2])
