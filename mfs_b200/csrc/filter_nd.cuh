@@ -357,8 +357,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
       }
       bool stop = done;
       double d_below = 0.0;                  // d[i+2] as left by the previous rotation
-      auto rotate = [&](const int i) {
-        const double e_i = qe[i], d_i = qd[i], d_up = qd[i + 1];
+      auto rotate = [&](const int i, const double e_i, const double d_i, const double d_up) {
         const double f = sn * e_i, b = cs * e_i;
         const double h2 = fma(f, f, g * g);
         if (h2 == 0.0) {                     // underflow: the matrix splits here
@@ -399,14 +398,29 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
         }
       };
       if constexpr (kRolled) {
+        // qd / qe live in local memory (run-time indices): rotation i reads (e[i], d[i]) one iteration ahead -- it does
+        // not modify them -- and takes d[i+1] from the previous iteration's d[i], so no load sits on the recurrence.
+        // (measured, profiles/r1_nd_prefetch_ab.log: +33 % at N = 6 (S = 21), -4 % at N = 5 (S = 15) -> S >= 21 only)
+        if constexpr (S >= 21) {
+          double e_nx = 0.0, d_nx = 0.0, d_carry = 0.0;
+          if (hi - 1 >= lo) { e_nx = qe[hi - 1]; d_nx = qd[hi - 1]; d_carry = qd[hi]; }
 #pragma unroll 1
-        for (int i = hi - 1; i >= lo; --i)
-          if (!stop && i < m && i >= l) rotate(i);
+          for (int i = hi - 1; i >= lo; --i) {
+            const double e_i = e_nx, d_i = d_nx, d_up = d_carry;
+            if (i > lo) { e_nx = qe[i - 1]; d_nx = qd[i - 1]; }
+            d_carry = d_i;
+            if (!stop && i < m && i >= l) rotate(i, e_i, d_i, d_up);
+          }
+        } else {
+#pragma unroll 1
+          for (int i = hi - 1; i >= lo; --i)
+            if (!stop && i < m && i >= l) rotate(i, qe[i], qd[i], qd[i + 1]);
+        }
       } else {
 #pragma unroll
         for (int i = S - 2; i >= 0; --i) {
           if (i < lo) break;
-          if (i < hi && !stop && i < m && i >= l) rotate(i);
+          if (i < hi && !stop && i < m && i >= l) rotate(i, qe[i], qd[i], qd[i + 1]);
         }
       }
       if (!done) {
