@@ -122,9 +122,10 @@ def cpu_baseline(N, T, target_seconds=15., threads=0, seed=666 + 1):
 
 
 def secondary_legs(device_index, fp64_peak):
-    """The other two kernels of the path, timed on the device (CUDA events, second of two runs), N=1 only:
-    the 2-D prey--predator moment filter (BASELINE configs[4] shape: N=5, central moments, TME-normal order 2) and one
-    time step of the brute-force grid filter at the paper's grid (n=2000, 100 sub-steps = 100 FP64 tensor-core GEMMs)."""
+    """The other kernels of the path, timed on the device (CUDA events, second of two runs), N=1 only:
+    the 2-D prey--predator moment filter (BASELINE configs[4] shape: N=5, central moments, TME-normal order 2), the data
+    simulator, the nell + gradient kernel, and one time step of the brute-force grid filter at the paper's grid
+    (n=2000, 100 sub-steps = 100 FP64 tensor-core GEMMs)."""
     import math
     import torch
     from mfs_b200 import _lib
@@ -179,6 +180,23 @@ def secondary_legs(device_index, fp64_peak):
                         'unit': 'trajectory-steps/s (each = 100 TME-3 Gaussian sub-steps + one Bernoulli draw)',
                         'config': f'{Bs} trajectories x T={Tb}, 100 sub-steps, Philox4x32-10 + Box-Muller in the kernel',
                         'kernel_ms': ms, 'sub_steps_per_s': Bs * Tb * 100 / (ms * 1e-3)}
+    # ---- nell + gradient in one pass (the objective of dardel/parameter_estimation/mf.py:37-54: well--Poisson, central
+    #      moments, TME-normal order 2, N = 7, T = 1000), next to the value-only kernel on the same records
+    from mfs_b200.one_dim.filtering import moment_filter_cms
+    from mfs_b200.one_dim.gradients import moment_filter_cms_value_and_grad
+    from mfs_b200.one_dim.moments import sde_cond_moments_tme_normal as tme_normal_1d
+    from mfs_b200.one_dim.ss_models import well_poisson
+    Ng, Bq = 7, 148 * 64 * 8
+    dtw, Tw, _, icw, driftw, dispw, _, pmfw, _ = well_poisson(3., Ng)
+    ysw = simulate_1d(driftw(3.), dispw, dtw, Tw, icw, pmfw(3.), Bq, 7, device=dev)[2]
+    famw = tme_normal_1d(driftw(3.), dispw, dtw, 2, Ng)
+    ms_v, _ = timed(lambda: moment_filter_cms(famw[1], famw[3], pmfw(3.), icw.cms, icw.mean, ysw, history='none'))
+    ms_g, rg = timed(lambda: moment_filter_cms_value_and_grad(famw[1], famw[3], pmfw(3.), icw.cms, icw.mean, ysw))
+    out['gradient'] = {'metric': 'well_poisson_nell_and_gradient_filter_steps_per_s', 'value': Bq * Tw / (ms_g * 1e-3),
+                       'unit': UNIT, 'config': f'N={Ng}, central, TME-normal order 2, {Bq} filters x T={Tw}, nell + d nell / d(theta1, theta2) '
+                                               f'by forward-mode duals in one kernel', 'kernel_ms': ms_g,
+                       'value_only_kernel_ms': ms_v, 'cost_vs_value_only': ms_g / ms_v,
+                       'finite_frac': float(torch.isfinite(rg[1]).all(dim=1).double().mean().item())}
     # ---- grid filter
     n, Bg, steps, Tg = 2000, 16384, 100, 1
     xs = np.linspace(-6., 6., n)
