@@ -346,6 +346,116 @@ MFS_DEV S measurement_pdf_t(int meas_id, double y, double lgam, const S& x, cons
 // ---------------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef MFS_GRAD_MIN_BLOCKS
+#define MFS_GRAD_MIN_BLOCKS 4
+#endif
+#ifdef MFS_GRAD_UNROLL_NODES
+#define MFS_NODE_LOOP _Pragma("unroll")
+#else
+#define MFS_NODE_LOOP _Pragma("unroll 1")
+#endif
+
+// Quadrature of a dual moment vector with the eigen-solve differentiated IMPLICITLY: the values go through the value
+// kernel's register QL (tridiag_ql_first_row), the tangents follow from first-order perturbation theory of the
+// symmetric tridiagonal eigenproblem J v_i = lambda_i v_i:
+//     d lambda_i = v_i^T dJ v_i,      d z_i = sum_{j != i} (v_j^T dJ v_i) / (lambda_i - lambda_j) z_j,   z_i = v_i[0],
+// with the eigenvectors rebuilt from (lambda_i, z_i) by the three-term recurrence of the orthonormal polynomials
+// (v_i[k] = z_i p_k(lambda_i) / p_0).  Jacobi matrices of positive measures have simple eigenvalues (beta_k > 0), so
+// the gaps never vanish.  Cost per tangent: N^3 + O(N^2) FMAs instead of pushing duals through ~2.3 N QL sweeps
+// (a dual rotation is ~105 FP64 instructions against 22).  Falls back to the dual QL when the fast QL does not converge.
+template <int N, int P>
+MFS_DEV bool quadrature_implicit(const Dual<P> (&ms)[2 * N], const Dual<P>& mean, Dual<P> (&w)[N], Dual<P> (&x)[N]) {
+  using S = Dual<P>;
+  S a[N], b[N];
+  if (!jacobi_from_moments_t<S, N>(ms, a, b)) return false;
+  double d[N], e[N], z[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { d[k] = a[k].v; e[k] = b[k].v; }
+  if (!tridiag_ql_first_row<N>(d, e, z)) {
+    S dd[N], ee[N], zz[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { dd[k] = a[k]; ee[k] = b[k]; }
+    const bool ok = tridiag_ql_t<S, N>(dd, ee, zz);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { w[i] = zz[i] * zz[i]; x[i] = dd[i] + mean; }
+    return ok;
+  }
+  // eigenvectors, V[i][k] = v_i[k] (run-time i: local memory), by the recurrence on the VALUES of (alpha, beta)
+  double V[N][N], lam[N], z0[N];
+  double rb[N];
+#pragma unroll
+  for (int k = 0; k + 1 < N; ++k) rb[k] = rcp_fast(b[k].v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { lam[i] = d[i]; z0[i] = z[i]; }
+  MFS_NODE_LOOP
+  for (int i = 0; i < N; ++i) {
+    const double li = lam[i];
+    double vm = 0.0, vk = z0[i];
+    V[i][0] = vk;
+#pragma unroll
+    for (int k = 0; k + 1 < N; ++k) {
+      const double vn = (fma(li - a[k].v, vk, (k > 0) ? -b[k > 0 ? k - 1 : 0].v * vm : 0.0)) * rb[k];
+      V[i][k + 1] = vn;
+      vm = vk;
+      vk = vn;
+    }
+  }
+  MFS_NODE_LOOP
+  for (int i = 0; i < N; ++i) {
+    double vi[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) vi[k] = V[i][k];
+    // u_p = dJ_p v_i for every tangent p
+    double u[P][N];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double t = a[k].d[p] * vi[k];
+        if (k > 0) t = fma(b[k > 0 ? k - 1 : 0].d[p], vi[k > 0 ? k - 1 : 0], t);
+        if (k + 1 < N) t = fma(b[k].d[p], vi[k + 1 < N ? k + 1 : k], t);
+        u[p][k] = t;
+      }
+    }
+    const double li = lam[i];
+    double dl[P], dz[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { dl[p] = 0.0; dz[p] = 0.0; }
+    MFS_NODE_LOOP
+    for (int j = 0; j < N; ++j) {
+      double c[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) c[p] = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double vjk = V[j][k];
+#pragma unroll
+        for (int p = 0; p < P; ++p) c[p] = fma(vjk, u[p][k], c[p]);
+      }
+      if (j == i) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) dl[p] = c[p];
+      } else {
+        const double gz = z0[j] * rcp_fast(li - lam[j]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) dz[p] = fma(c[p], gz, dz[p]);
+      }
+    }
+    const double zi = z0[i];
+    S wi, xi;
+    wi.v = zi * zi;
+    xi.v = li + mean.v;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      wi.d[p] = 2.0 * zi * dz[p];
+      xi.d[p] = dl[p] + mean.d[p];
+    }
+    w[i] = wi;
+    x[i] = xi;
+  }
+  return true;
+}
+
 template <class S, int N>
 MFS_DEV bool quadrature_t(const S (&ms)[2 * N], const S& mean, S (&w)[N], S (&x)[N]) {
   S d[N], e[N], z[N];   // registers (compile-time indices); w / x are the caller's atom arrays (local memory)
@@ -360,13 +470,14 @@ MFS_DEV bool quadrature_t(const S (&ms)[2 * N], const S& mean, S (&w)[N], S (&x)
   return ok;
 }
 
-#ifndef MFS_GRAD_MIN_BLOCKS
-#define MFS_GRAD_MIN_BLOCKS 4
-#endif
-#ifdef MFS_GRAD_UNROLL_NODES
-#define MFS_NODE_LOOP _Pragma("unroll")
+// Default: duals through the QL iteration.  -DMFS_GRAD_IMPLICIT_EIG selects quadrature_implicit (same results, all
+// gradient tests green), measured 1.55x SLOWER in this first form at N = 7 (160 vs 103 ms, profiles/r1_grad_probe_v3.log):
+// its N^2 dot products are dependent FMA chains over eigenvectors in local memory, whereas a dual rotation has three
+// independent components in registers.
+#ifdef MFS_GRAD_IMPLICIT_EIG
+#define MFS_GRAD_QUADRATURE quadrature_implicit<N, P>
 #else
-#define MFS_NODE_LOOP _Pragma("unroll 1")
+#define MFS_GRAD_QUADRATURE quadrature_t<S, N>
 #endif
 
 template <int N, int P>
@@ -397,7 +508,7 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
 #pragma unroll
   for (int p = 0; p < 2 * N; ++p) ms[p] = make_dual<P>(A.ms0[b * A.ms0_stride + p]);
   int32_t status = -1;
-  bool ok = quadrature_t<S, N>(ms, mean, w, x);   // filtering.py:78 / :145 at k = 0
+  bool ok = MFS_GRAD_QUADRATURE(ms, mean, w, x);   // filtering.py:78 / :145 at k = 0
   if (!ok) status = 0;
 
   for (int64_t t = 0; t < A.T && ok; ++t) {
@@ -475,7 +586,7 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
       for (int p = 2; p < 2 * N; ++p) { f *= (double)p; ms[p] = ms[p] * f; }
     }
     // ---- update (filtering.py:81-86 / :150-158)
-    ok = quadrature_t<S, N>(ms, central ? mean : make_dual<P>(0.0), w, x);
+    ok = MFS_GRAD_QUADRATURE(ms, central ? mean : make_dual<P>(0.0), w, x);
     if (!ok) { status = (int32_t)t; break; }
     const double lgam = (A.meas_id == MFS_MEAS_POISSON_SOFTPLUS) ? lgamma(y + 1.0) : 0.0;
     S cc = make_dual<P>(0.0);
