@@ -380,32 +380,27 @@ MFS_DEV bool quadrature_implicit(const Dual<P> (&ms)[2 * N], const Dual<P>& mean
     for (int i = 0; i < N; ++i) { w[i] = zz[i] * zz[i]; x[i] = dd[i] + mean; }
     return ok;
   }
-  // eigenvectors, V[i][k] = v_i[k] (run-time i: local memory), by the recurrence on the VALUES of (alpha, beta)
-  double V[N][N], lam[N], z0[N];
+  // Eigenvectors are never stored: v_j[k] = z_j p_k(lambda_j) / p_0 is regenerated by the three-term recurrence on the
+  // VALUES of (alpha, beta) while the dot products v_j . (dJ v_i) accumulate -- all N vectors v_j advance together
+  // (N independent chains, compile-time j and k: registers), only the outer index i is a run-time loop.
+  double lam_l[N], z_l[N];     // run-time indexed copies (local memory)
   double rb[N];
 #pragma unroll
   for (int k = 0; k + 1 < N; ++k) rb[k] = rcp_fast(b[k].v);
 #pragma unroll
-  for (int i = 0; i < N; ++i) { lam[i] = d[i]; z0[i] = z[i]; }
+  for (int i = 0; i < N; ++i) { lam_l[i] = d[i]; z_l[i] = z[i]; }
   MFS_NODE_LOOP
   for (int i = 0; i < N; ++i) {
-    const double li = lam[i];
-    double vm = 0.0, vk = z0[i];
-    V[i][0] = vk;
+    const double li = lam_l[i], zi = z_l[i];
+    // v_i and u_p = dJ_p v_i
+    double vi[N];
+    vi[0] = zi;
 #pragma unroll
     for (int k = 0; k + 1 < N; ++k) {
-      const double vn = (fma(li - a[k].v, vk, (k > 0) ? -b[k > 0 ? k - 1 : 0].v * vm : 0.0)) * rb[k];
-      V[i][k + 1] = vn;
-      vm = vk;
-      vk = vn;
+      double t = (li - a[k].v) * vi[k];
+      if (k > 0) t = fma(-b[k > 0 ? k - 1 : 0].v, vi[k > 0 ? k - 1 : 0], t);
+      vi[k + 1] = t * rb[k];
     }
-  }
-  MFS_NODE_LOOP
-  for (int i = 0; i < N; ++i) {
-    double vi[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) vi[k] = V[i][k];
-    // u_p = dJ_p v_i for every tangent p
     double u[P][N];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -417,31 +412,44 @@ MFS_DEV bool quadrature_implicit(const Dual<P> (&ms)[2 * N], const Dual<P>& mean
         u[p][k] = t;
       }
     }
-    const double li = lam[i];
+    double vm[N], vk[N], c[P][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      vm[j] = 0.0;
+      vk[j] = z[j];
+#pragma unroll
+      for (int p = 0; p < P; ++p) c[p][j] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) c[p][j] = fma(vk[j], u[p][k], c[p][j]);
+      }
+      if (k + 1 < N) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double t = (d[j] - a[k].v) * vk[j];
+          if (k > 0) t = fma(-b[k > 0 ? k - 1 : 0].v, vm[j], t);
+          vm[j] = vk[j];
+          vk[j] = t * rb[k];
+        }
+      }
+    }
     double dl[P], dz[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) { dl[p] = 0.0; dz[p] = 0.0; }
-    MFS_NODE_LOOP
+#pragma unroll
     for (int j = 0; j < N; ++j) {
-      double c[P];
+      const bool self = (j == i);
+      const double gz = self ? 0.0 : z[j] * rcp_fast(li - d[j]);
 #pragma unroll
-      for (int p = 0; p < P; ++p) c[p] = 0.0;
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double vjk = V[j][k];
-#pragma unroll
-        for (int p = 0; p < P; ++p) c[p] = fma(vjk, u[p][k], c[p]);
-      }
-      if (j == i) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) dl[p] = c[p];
-      } else {
-        const double gz = z0[j] * rcp_fast(li - lam[j]);
-#pragma unroll
-        for (int p = 0; p < P; ++p) dz[p] = fma(c[p], gz, dz[p]);
+      for (int p = 0; p < P; ++p) {
+        dl[p] = self ? c[p][j] : dl[p];
+        dz[p] = fma(c[p][j], gz, dz[p]);
       }
     }
-    const double zi = z0[i];
     S wi, xi;
     wi.v = zi * zi;
     xi.v = li + mean.v;
@@ -471,9 +479,8 @@ MFS_DEV bool quadrature_t(const S (&ms)[2 * N], const S& mean, S (&w)[N], S (&x)
 }
 
 // Default: duals through the QL iteration.  -DMFS_GRAD_IMPLICIT_EIG selects quadrature_implicit (same results, all
-// gradient tests green), measured 1.55x SLOWER in this first form at N = 7 (160 vs 103 ms, profiles/r1_grad_probe_v3.log):
-// its N^2 dot products are dependent FMA chains over eigenvectors in local memory, whereas a dual rotation has three
-// independent components in registers.
+// gradient tests green), measured SLOWER at N = 7 (146 vs 103 ms, profiles/r1_grad_probe_v4_implicit.log and
+// r1_ncu_filter1d_grad_N7_implicit.md; analysis in DESIGN.md section 5b).
 #ifdef MFS_GRAD_IMPLICIT_EIG
 #define MFS_GRAD_QUADRATURE quadrature_implicit<N, P>
 #else
