@@ -71,6 +71,7 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
   const double c = 0.5 * P.dispersion * P.dispersion;
   const double dt = P.dt;
   double tn[N];  // Benes: tanh at the nodes, kept between the two passes
+  double mu_n[N], var_n[N];  // Normal families, central mode: (mean, var) at the nodes, kept between the two passes
 
   // pass 1: predicted mean (and scale) -- filtering.py:146-147, :223-224
   if (KIND == KIND_BENES_TME) {
@@ -87,10 +88,10 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
         mu = fma(dt, tn[i], x[i]);
         var = (P.tme_order >= 2) ? fma(dt * dt, fma(-tn[i], tn[i], 1.0), dt) : dt;
       } else if (KIND == KIND_NORMAL) {
+        // (state_cond_mean of the tme_normal factory is tme.expectation(identity): the same expansion as the mean)
         normal_mean_var(P.trans_id, P.drift_id, P.tme_order, x[i], c, dt, tprm, mu, var);
-        if (P.trans_id == MFS_TRANS_TME_NORMAL) {
-          // state_cond_mean of the tme_normal factory is tme.expectation(identity): same expansion as mean
-        }
+        mu_n[i] = mu;
+        var_n[i] = var;
       } else {
         const Jet j = drift_jet(P.drift_id, x[i], tprm);
         tme_mean_var(j, x[i], c, dt, P.tme_order, mu, var);
@@ -179,7 +180,12 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double mu, var;
-      normal_mean_var(P.trans_id, P.drift_id, P.tme_order, x[i], c, dt, tprm, mu, var);
+      if (MODE == MFS_MODE_RAW) {
+        normal_mean_var(P.trans_id, P.drift_id, P.tme_order, x[i], c, dt, tprm, mu, var);
+      } else {   // computed by pass 1
+        mu = mu_n[i];
+        var = var_n[i];
+      }
       mu = (MODE == MFS_MODE_RAW) ? mu : mu - mean;
       if (var < 0.0) mu = nan("");  // variance**((p-m)/2) * 0. is NaN for every p >= 1 in the reference
       double m2 = 1.0, m1 = mu;
