@@ -220,3 +220,20 @@ def test_edge_shapes():
     bad[2] = -1e-3
     nbad, gbad, sbad = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(3.), bad, ic.mean, dev(ys), return_status=True)
     assert bool(torch.isnan(nbad).all()) and bool(torch.isnan(gbad).all()) and bool((sbad == 0).all())
+
+
+@pytest.mark.parametrize('N,T', [(4, 30), (6, 40)])
+def test_gradient_against_complex_step_of_the_dense_algorithm(N, T):
+    """Independent route to the reference's jax.grad: the complex-step derivative of a restatement of its DENSE
+    algorithm in analytic arithmetic (oracle/mfs_oracle_grad.py; no finite-difference noise).  Tolerance = the
+    conditioning floor of the recursion, not a differencing error."""
+    from oracle import mfs_oracle_grad as G
+    dt, _, ts, ic, drift, disp, emission, pmf, _ = well_poisson(3., N)
+    ys = synthetic.well_poisson_ys_numpy(3, T, 680 + N)
+    theta = (2.7, 3.4)
+    fam = sde_cond_moments_tme_normal(drift(theta[0]), disp, dt, 2, N)
+    nell, grad = moment_filter_cms_value_and_grad(fam[1], fam[3], pmf(theta[1]), ic.cms, ic.mean, dev(ys))
+    ref = [G.well_poisson_value_and_grad(theta[0], theta[1], ic.cms, ic.mean, ys[k], dt=dt) for k in range(3)]
+    np.testing.assert_allclose(nell.cpu().numpy(), [r[0] for r in ref], rtol=1e-10)
+    g_ref = np.stack([r[1] for r in ref])
+    np.testing.assert_allclose(grad.cpu().numpy(), g_ref, rtol=1e-7, atol=1e-7 * np.abs(g_ref).max())
