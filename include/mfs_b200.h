@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MFS_ABI_VERSION 2
+#define MFS_ABI_VERSION 3
 #define MFS_MAX_N 15          /* quadrature nodes; 2N moments.  Reference sweeps N=2..15 (dardel/run_time_profile.sh:25) */
 #define MFS_MAX_PARAMS 4
 
@@ -66,7 +66,12 @@ enum { MFS_YS_U8 = 0, MFS_YS_I32 = 1, MFS_YS_F64 = 2 };
 enum {
   MFS_OUT_FULL = 0, /* every step: ms_out[b][t][0..2N) (+ mean_out[b][t], scale_out[b][t]) like the reference */
   MFS_OUT_LAST = 1, /* only the final step's moments (ms_out[b][0..2N)), mean, scale                          */
-  MFS_OUT_NONE = 2  /* only nell (parameter-estimation objective, dardel/parameter_estimation/mf.py:52)       */
+  MFS_OUT_NONE = 2, /* only nell (parameter-estimation objective, dardel/parameter_estimation/mf.py:52)       */
+  MFS_OUT_MEANVAR = 3 /* every step: (mean, variance) of the filtering distribution, ms_out[b][t][0..2) -- what the
+                         reference's consumers read from the history (dardel/prey_predator/mf.py:84-88,
+                         dardel/benes_bernoulli/post_processing_mf.py:41-66): 16 B per step instead of 16 N.
+                         raw: (m1, m2 - m1^2); central: (mean, cm2); scaled: (mean, scale^2 scm2).
+                         mean_out / scale_out are not written. */
 };
 
 /* flags.
@@ -109,7 +114,8 @@ typedef struct mfs_filter1d_args {
   int64_t ys_stride_b;
   int64_t ys_stride_t;
 
-  double* ms_out;        /* FULL: [B][T][2N] via strides below; LAST: [B][2N] (ms_stride_t ignored) */
+  double* ms_out;        /* FULL: [B][T][2N] via strides below; LAST: [B][2N] (ms_stride_t ignored);
+                            MEANVAR: [B][T][2] via the same strides */
   int64_t ms_stride_b;
   int64_t ms_stride_t;
   double* mean_out;      /* FULL: [B][T] (stride_b = aux_stride_b, stride_t = 1); LAST: [B]; may be NULL in RAW mode */
@@ -125,6 +131,21 @@ typedef struct mfs_filter1d_args {
    * Results are identical with and without; NULL = one launch for the whole scan. */
   void* workspace;
   int64_t workspace_bytes;
+  /* Time-chunked execution (checkpoint / resume): the scan of one record set may be cut into calls over consecutive
+   * blocks of measurements.  carry_out (device, [B][4N + 4] doubles, may be NULL) receives the filter state after the
+   * last step of this call; handing it to the next call as carry_in (may be NULL = start from ms0 / mean0 / scale0,
+   * which are then ignored) continues the scan bit-identically to one long call.  nell_out is the running total.
+   * Layout of one state: ms[2N], atom weights[N], atom nodes[N], mean, scale, nell, flag (flag < 0: the filter failed
+   * at absolute step -flag - 1 and stays NaN).  t_offset = absolute index of this call's first step (only used for
+   * the step index reported in status_out).  mfs_filter_1d (device pointers) only. */
+  const double* carry_in;
+  double* carry_out;
+  int64_t t_offset;
+  /* Parameter grids over shared records (the theta grid of dardel/parameter_estimation/mf.py's objective): with
+   * grid_records = P > 0 the batch is a (B / P) x P grid, filter b = g P + j reads record j (ys + j ys_stride_b) and
+   * row g of every per-filter input table (ms0, mean0, scale0, trans_params, meas_params: stride x g).  Outputs stay
+   * indexed by b.  0 = one record and one table row per filter.  mfs_filter_1d (device pointers) only. */
+  int64_t grid_records;
 } mfs_filter1d_args;
 
 /* Scratch size in bytes for mfs_filter_1d's segmented execution (-1 for invalid arguments). */

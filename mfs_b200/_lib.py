@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MFS_B200_LIB') or os.path.join(_HERE, 'libmfs_b200.so')   # env override: tuning builds
 CSRC = os.path.join(_HERE, 'csrc')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_N = 15
 MAX_PARAMS = 4
 
@@ -20,7 +20,7 @@ TRANS = {'tme': 0, 'tme_normal': 1, 'euler': 2, 'normal_affine': 3}
 DRIFT = {'benes': 0, 'well': 1, 'linear': 2}
 MEAS = {'bernoulli_logistic_cubic': 0, 'poisson_softplus': 1, 'gaussian': 2}
 YS_DTYPE = {'uint8': 0, 'bool': 0, 'int32': 1, 'float64': 2}
-OUT_MODE = {'full': 0, 'last': 1, 'none': 2}
+OUT_MODE = {'full': 0, 'last': 1, 'none': 2, 'meanvar': 3}
 FLAG_RECOMPUTE_PREDICT_QUADRATURE = 1
 GRAD_MAX_TANGENTS = 2
 
@@ -45,6 +45,8 @@ class Filter1dArgs(ctypes.Structure):
         ('nell_out', ctypes.c_void_p), ('status_out', ctypes.c_void_p),
         ('flags', ctypes.c_int32), ('segment_steps', ctypes.c_int32),
         ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
+        ('carry_in', ctypes.c_void_p), ('carry_out', ctypes.c_void_p), ('t_offset', ctypes.c_int64),
+        ('grid_records', ctypes.c_int64),
     ]
 
 

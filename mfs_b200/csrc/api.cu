@@ -45,6 +45,15 @@ static cudaError_t ws_alloc(int device, size_t bytes, void** out) {
   std::lock_guard<std::mutex> lock(g_ws_mutex);
   for (WsBlock& b : g_ws)
     if (!b.busy && b.device == device && b.bytes == bytes) { b.busy = true; *out = b.ptr; return cudaSuccess; }
+  // a miss means the shapes changed: idle big blocks of the old shapes go back to the driver instead of accumulating
+  for (size_t i = 0; i < g_ws.size();) {
+    if (!g_ws[i].busy && g_ws[i].device == device && g_ws[i].bytes >= (64u << 20)) {
+      cudaFree(g_ws[i].ptr);
+      g_ws.erase(g_ws.begin() + i);
+    } else {
+      ++i;
+    }
+  }
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) {   // give cached idle blocks back and retry once
@@ -87,10 +96,7 @@ static int validate(const mfs_filter1d_args* a) {
     return fail("tme_order=%d outside [1, 3]", a->tme_order);
   if (a->meas_id < MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC || a->meas_id > MFS_MEAS_GAUSSIAN) return fail("unknown meas_id %d", a->meas_id);
   if (a->ys_dtype < MFS_YS_U8 || a->ys_dtype > MFS_YS_F64) return fail("unknown ys_dtype %d", a->ys_dtype);
-  if (a->out_mode < MFS_OUT_FULL || a->out_mode > MFS_OUT_NONE) return fail("unknown out_mode %d", a->out_mode);
-  if (a->mode == MFS_MODE_SCALED && a->trans_id != MFS_TRANS_TME)
-    return fail("scaled central moments are only offered with the TME family: the reference's scaled Normal/Euler "
-                "factories divide every order by prod(scale**k) (mfs/one_dim/moments.py:205,243)");
+  if (a->out_mode < MFS_OUT_FULL || a->out_mode > MFS_OUT_MEANVAR) return fail("unknown out_mode %d", a->out_mode);
   if (!(a->dt > 0.0)) return fail("dt must be > 0");
   if (a->B == 0) return 0;
   if (!a->ms0 || !a->trans_params || !a->meas_params || !a->nell_out) return fail("ms0 / trans_params / meas_params / nell_out must not be NULL");
@@ -98,23 +104,35 @@ static int validate(const mfs_filter1d_args* a) {
   if (a->mode != MFS_MODE_RAW && !a->mean0) return fail("mean0 is NULL in central/scaled mode");
   if (a->mode == MFS_MODE_SCALED && !a->scale0) return fail("scale0 is NULL in scaled mode");
   if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
-  if (a->out_mode != MFS_OUT_NONE && a->mode != MFS_MODE_RAW && !a->mean_out) return fail("mean_out is NULL in central/scaled mode");
-  if (a->out_mode != MFS_OUT_NONE && a->mode == MFS_MODE_SCALED && !a->scale_out) return fail("scale_out is NULL in scaled mode");
+  const bool aux = a->out_mode == MFS_OUT_FULL || a->out_mode == MFS_OUT_LAST;
+  if (aux && a->mode != MFS_MODE_RAW && !a->mean_out) return fail("mean_out is NULL in central/scaled mode");
+  if (aux && a->mode == MFS_MODE_SCALED && !a->scale_out) return fail("scale_out is NULL in scaled mode");
+  if (a->t_offset < 0) return fail("negative t_offset");
+  if (a->grid_records < 0 || (a->grid_records > 0 && a->B % a->grid_records != 0))
+    return fail("grid_records=%lld must be 0 or a divisor of B=%lld", (long long)a->grid_records, (long long)a->B);
   return 0;
 }
 
-static int pick_kind(const mfs_filter1d_args& a) {
+// Compile-time specialisations: the headline model (Benes TME + Bernoulli-logistic likelihood) and the estimation
+// objective (Normal family + Poisson-softplus likelihood); everything else runs the run-time-switched instances.
+static int pick_kind(const mfs_filter1d_args& a, int* meas_ct) {
+  *meas_ct = -1;
   if (a.trans_id == MFS_TRANS_TME) {
-    if (a.drift_id == MFS_DRIFT_BENES && a.dispersion == 1.0) return KIND_BENES_TME;
+    if (a.drift_id == MFS_DRIFT_BENES && a.dispersion == 1.0 && a.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
+      *meas_ct = MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC;
+      return KIND_BENES_TME;
+    }
     return KIND_TME;
   }
+  if (a.meas_id == MFS_MEAS_POISSON_SOFTPLUS) *meas_ct = MFS_MEAS_POISSON_SOFTPLUS;
   return KIND_NORMAL;
 }
 
 static cudaError_t dispatch(const mfs_filter1d_args& a, const SegInfo& g, cudaStream_t s) {
-  const int kind = pick_kind(a);
+  int meas_ct = -1;
+  const int kind = pick_kind(a, &meas_ct);
   switch (a.N) {
-#define MFS_CASE(n) case n: return launch_filter1d<n>(a, g, kind, s);
+#define MFS_CASE(n) case n: return launch_filter1d<n>(a, g, kind, meas_ct, s);
     MFS_CASE(2) MFS_CASE(3) MFS_CASE(4) MFS_CASE(5) MFS_CASE(6) MFS_CASE(7) MFS_CASE(8) MFS_CASE(9)
     MFS_CASE(10) MFS_CASE(11) MFS_CASE(12) MFS_CASE(13) MFS_CASE(14) MFS_CASE(15)
 #undef MFS_CASE
@@ -133,39 +151,91 @@ __global__ void __launch_bounds__(128) nan_fill_kernel(const mfs_filter1d_args P
   const int64_t b = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= P.B) return;
-  const int s = P.status_out[b];
+  int64_t s = P.status_out[b];
   if (s < 0) return;
-  const int M = 2 * P.N;
+  s -= P.t_offset;             // status holds the absolute step; a filter that failed in an earlier chunk starts at 0
+  if (s < 0) s = 0;
+  const int M = (P.out_mode == MFS_OUT_MEANVAR) ? 2 : 2 * P.N;
   const double qnan = nan("");
   double* o = P.ms_out + b * P.ms_stride_b;
   if (P.ms_stride_t == M) {
-    double* base = o + (int64_t)s * M;
+    double* base = o + s * M;
     const int64_t cnt = (P.T - s) * M;
     for (int64_t e = lane; e < cnt; e += 32) base[e] = qnan;
   } else {
     for (int64_t t = s; t < P.T; ++t)
       for (int p = lane; p < M; p += 32) o[t * P.ms_stride_t + p] = qnan;
   }
+  if (P.out_mode == MFS_OUT_MEANVAR) return;
   if (P.mode != MFS_MODE_RAW && P.mean_out)
     for (int64_t t = s + lane; t < P.T; t += 32) P.mean_out[b * P.aux_stride_b + t] = qnan;
   if (P.mode == MFS_MODE_SCALED && P.scale_out)
     for (int64_t t = s + lane; t < P.T; t += 32) P.scale_out[b * P.aux_stride_b + t] = qnan;
 }
 
+// T == 0 (or a carried state with nothing to filter): the reference returns empty histories and nell = 0; with a
+// carry the state passes through unchanged.
+__global__ void __launch_bounds__(128) empty_scan_kernel(const mfs_filter1d_args P, int state_doubles) {
+  const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (b >= P.B) return;
+  const int64_t row = P.grid_records > 0 ? b / P.grid_records : b;
+  double nell = 0.0;
+  int status = -1;
+  if (P.carry_in) {
+    const double* ci = P.carry_in + b * state_doubles;
+    nell = ci[state_doubles - 2];
+    const double flag = ci[state_doubles - 1];
+    if (flag < 0.0) { status = (int)(-flag) - 1; nell = nan(""); }
+    if (P.carry_out)
+      for (int k = 0; k < state_doubles; ++k) P.carry_out[b * state_doubles + k] = ci[k];
+  } else if (P.carry_out) {
+    const int M = 2 * P.N;
+    double* co = P.carry_out + b * state_doubles;
+    for (int k = 0; k < M; ++k) co[k] = P.ms0[row * P.ms0_stride + k];
+    for (int k = M; k < 2 * M; ++k) co[k] = 0.0;
+    co[2 * M] = P.mode != MFS_MODE_RAW ? P.mean0[row * P.mean0_stride] : 0.0;
+    co[2 * M + 1] = P.mode == MFS_MODE_SCALED ? P.scale0[row * P.scale0_stride] : 1.0;
+    co[2 * M + 2] = 0.0;
+    co[2 * M + 3] = 0.0;
+  }
+  if (P.out_mode == MFS_OUT_LAST) {
+    // no step ran: the "last" moments are the initial ones
+    const int M = 2 * P.N;
+    const double* src = P.carry_in ? P.carry_in + b * state_doubles : P.ms0 + row * P.ms0_stride;
+    for (int k = 0; k < M; ++k) P.ms_out[b * P.ms_stride_b + k] = src[k];
+    if (P.mode != MFS_MODE_RAW && P.mean_out)
+      P.mean_out[b * P.aux_stride_b] = P.carry_in ? P.carry_in[b * state_doubles + 2 * M] : P.mean0[row * P.mean0_stride];
+    if (P.mode == MFS_MODE_SCALED && P.scale_out)
+      P.scale_out[b * P.aux_stride_b] = P.carry_in ? P.carry_in[b * state_doubles + 2 * M + 1] : P.scale0[row * P.scale0_stride];
+  }
+  P.nell_out[b] = nell;
+  if (P.status_out) P.status_out[b] = status;
+}
+
 constexpr int64_t kDefaultSegmentSteps = 64;
 
 static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
   if (a.B == 0) return 0;
+  const bool per_step = a.out_mode == MFS_OUT_FULL || a.out_mode == MFS_OUT_MEANVAR;
   if (a.out_mode != MFS_OUT_NONE) {
-    if ((reinterpret_cast<uintptr_t>(a.ms_out) & 15) || (a.ms_stride_b & 1) ||
-        (a.out_mode == MFS_OUT_FULL && (a.ms_stride_t & 1)))
+    if ((reinterpret_cast<uintptr_t>(a.ms_out) & 15) || (a.ms_stride_b & 1) || (per_step && (a.ms_stride_t & 1)))
       return fail("ms_out must be 16-byte aligned with even strides (vector stores)");
   }
   if (a.B > (int64_t)kBlock * 0x7fffffffLL) return fail("B too large for one launch");
+  if (a.T == 0) {   // nothing to scan: empty histories, nell = 0 (the reference's scan over an empty ys)
+    empty_scan_kernel<<<(unsigned)((a.B + 127) / 128), 128, 0, s>>>(a, 4 * a.N + 4);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return fail("empty-scan launch failed: %s", cudaGetErrorString(e0));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
   SegInfo g = {};
   g.t0 = 0;
   g.t1 = a.T;
-  g.defer_nan_fill = (a.out_mode == MFS_OUT_FULL && a.status_out != nullptr && a.T > 1) ? 1 : 0;
+  g.state_in = a.carry_in;
+  g.state_out = a.carry_out;
+  g.last = 1;
+  g.defer_nan_fill = (per_step && a.status_out != nullptr && a.T > 1) ? 1 : 0;
   auto fill_tails = [&]() -> int {
     if (!g.defer_nan_fill) return 0;
     const int64_t ctas = (a.B * 32 + 127) / 128;
@@ -188,7 +258,7 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
   if (a.workspace_bytes < need) return fail("workspace too small: %lld < %lld bytes", (long long)a.workspace_bytes, (long long)need);
   const int64_t nseg = (a.T + seg - 1) / seg;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(a.workspace) + 255) & ~uintptr_t(255));
-  g.state = reinterpret_cast<double*>(base);
+  double* park = reinterpret_cast<double*>(base);
   const size_t state_bytes = ((size_t)a.B * (4 * a.N + 4) * sizeof(double) + 255) & ~size_t(255);
   int32_t* idx[2] = {reinterpret_cast<int32_t*>(base + state_bytes),
                      reinterpret_cast<int32_t*>(base + state_bytes + (((size_t)a.B * 4 + 255) & ~size_t(255)))};
@@ -196,12 +266,16 @@ static int launch_device(const mfs_filter1d_args& a, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(nseg + 1), s);
   if (e != cudaSuccess) return fail("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
   for (int64_t k = 0; k < nseg; ++k) {
+    const bool last = k + 1 == nseg;
     g.t0 = k * seg;
-    g.t1 = (k + 1 == nseg) ? a.T : (k + 1) * seg;
+    g.t1 = last ? a.T : (k + 1) * seg;
     g.idx_in = k == 0 ? nullptr : idx[(k - 1) & 1];
     g.count_in = k == 0 ? nullptr : counts + k;
-    g.idx_out = (k + 1 == nseg) ? nullptr : idx[k & 1];
-    g.count_out = (k + 1 == nseg) ? nullptr : counts + k + 1;
+    g.idx_out = last ? nullptr : idx[k & 1];
+    g.count_out = last ? nullptr : counts + k + 1;
+    g.state_in = k == 0 ? a.carry_in : park;
+    g.state_out = last ? a.carry_out : park;
+    g.last = last ? 1 : 0;
     e = dispatch(a, g, s);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   }
@@ -361,6 +435,8 @@ int mfs_filter_1d_grad(const mfs_filter1d_args* a, int32_t n_tangents, const int
   if (int rc = validate(a)) return rc;
   if (a->mode == MFS_MODE_SCALED) return fail("mfs_filter_1d_grad: raw and central moments only");
   if (a->stable) return fail("mfs_filter_1d_grad: stable=True is not differentiable (eps-substituted pivots); not offered");
+  if (a->carry_in || a->carry_out || a->grid_records || a->t_offset)
+    return fail("mfs_filter_1d_grad: carry_in / carry_out / t_offset / grid_records are not offered by the gradient kernel");
   if (n_tangents < 1 || n_tangents > MFS_GRAD_MAX_TANGENTS) return fail("mfs_filter_1d_grad: n_tangents=%d outside [1, %d]", n_tangents, MFS_GRAD_MAX_TANGENTS);
   if (!tangent_ids) return fail("mfs_filter_1d_grad: tangent_ids must not be NULL");
   if (a->B == 0) return 0;
@@ -393,20 +469,34 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
   if (a->B == 0) return 0;
   const int M = 2 * a->N;
   const int64_t T = a->T;
+  if (a->carry_in || a->carry_out) return fail("carry_in / carry_out are offered by mfs_filter_1d (device pointers) only");
+  if (a->grid_records) return fail("grid_records is offered by mfs_filter_1d (device pointers) only");
   if (a->T > 0 && (a->ys_stride_t != 1 || a->ys_stride_b != T)) return fail("host ys must be contiguous (B, T)");
   if (a->out_mode == MFS_OUT_FULL && (a->ms_stride_t != M || a->ms_stride_b != T * M || a->aux_stride_b != T))
     return fail("host outputs must be contiguous (B, T, 2N) / (B, T)");
+  if (a->out_mode == MFS_OUT_MEANVAR && (a->ms_stride_t != 2 || a->ms_stride_b != T * 2))
+    return fail("host outputs must be contiguous (B, T, 2)");
   if (a->out_mode == MFS_OUT_LAST && (a->ms_stride_b != M || a->aux_stride_b != 1))
     return fail("host outputs must be contiguous (B, 2N) / (B,)");
+  // every per-filter table is copied chunk-wise with its natural row length: check the strides before anything is queued
+  if (a->ms0_stride != 0 && a->ms0_stride != M) return fail("host ms0 must be contiguous (B, 2N) or shared (stride 0)");
+  if ((a->trans_param_stride != 0 && a->trans_param_stride != MFS_MAX_PARAMS) ||
+      (a->meas_param_stride != 0 && a->meas_param_stride != MFS_MAX_PARAMS))
+    return fail("host params must be contiguous (B, %d) or shared (stride 0)", MFS_MAX_PARAMS);
+  if (a->mean0 && a->mean0_stride != 0 && a->mean0_stride != 1) return fail("host mean0 must be contiguous (B,) or shared (stride 0)");
+  if (a->scale0 && a->scale0_stride != 0 && a->scale0_stride != 1) return fail("host scale0 must be contiguous (B,) or shared (stride 0)");
   MFS_CUDA(cudaSetDevice(device));
 
   const int esz = ys_elem_size(a->ys_dtype);
+  const int64_t row_out = a->out_mode == MFS_OUT_FULL ? T * (M + 2) * 8 : a->out_mode == MFS_OUT_MEANVAR ? T * 16 : (M + 4) * 8;
+  const int64_t per_filter = row_out + T * esz + (4 * a->N + 12) * 8;
   if (chunk_filters <= 0) {
-    // ~1 GiB of traffic per chunk, but never fewer than two CTAs per SM (the D2H copy, not the kernel, is the
-    // bottleneck of the full-history mode: small chunks shorten the un-overlapped head and tail of the pipeline)
-    const int64_t per_filter = (a->out_mode == MFS_OUT_FULL ? T * (M + 2) * 8 : (M + 4) * 8) + T * esz;
-    chunk_filters = (1LL << 30) / (per_filter > 0 ? per_filter : 1);
-    if (chunk_filters < 148LL * 2 * kBlock) chunk_filters = 148LL * 2 * kBlock;
+    // ~1 GiB of staging per chunk; at least two CTAs per SM when that still fits 4 GiB (the D2H copy, not the kernel,
+    // is the bottleneck of the full-history mode: small chunks shorten the un-overlapped head and tail of the pipeline)
+    chunk_filters = (1LL << 30) / per_filter;
+    const int64_t floor_filters = 148LL * 2 * kBlock;
+    if (chunk_filters < floor_filters) chunk_filters = ((4LL << 30) / per_filter < floor_filters) ? (4LL << 30) / per_filter : floor_filters;
+    if (chunk_filters < kBlock) chunk_filters = kBlock;
   }
   chunk_filters = (chunk_filters + kBlock - 1) / kBlock * kBlock;
   if (chunk_filters > a->B) chunk_filters = a->B;
@@ -423,7 +513,8 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
   const bool per_ms0 = a->ms0_stride != 0, per_mean0 = a->mean0 && a->mean0_stride != 0,
              per_scale0 = a->scale0 && a->scale0_stride != 0, per_t = a->trans_param_stride != 0,
              per_m = a->meas_param_stride != 0;
-  const int64_t out_ms = a->out_mode == MFS_OUT_FULL ? C * T * M : a->out_mode == MFS_OUT_LAST ? C * M : 0;
+  const int64_t out_ms = a->out_mode == MFS_OUT_FULL ? C * T * M : a->out_mode == MFS_OUT_LAST ? C * M
+                         : a->out_mode == MFS_OUT_MEANVAR ? C * T * 2 : 0;
   const int64_t out_aux = a->out_mode == MFS_OUT_FULL ? C * T : a->out_mode == MFS_OUT_LAST ? C : 0;
 
   int rc = 0;
@@ -489,16 +580,14 @@ int mfs_filter_1d_host(const mfs_filter1d_args* a, int device, int64_t chunk_fil
     d.ms_out = s.ms_out; d.mean_out = s.mean_out; d.scale_out = s.scale_out;
     d.nell_out = s.nell; d.status_out = s.status;
     d.workspace = s.seg_ws; d.workspace_bytes = seg_bytes; d.segment_steps = (int32_t)(seg_bytes > 0 ? seg_len : 0);
-    if (per_ms0 && a->ms0_stride != M) { rc = fail("host ms0 must be contiguous (B, 2N)"); cleanup(); return rc; }
-    if ((per_t && a->trans_param_stride != MFS_MAX_PARAMS) || (per_m && a->meas_param_stride != MFS_MAX_PARAMS)) {
-      rc = fail("host params must be contiguous (B, %d)", MFS_MAX_PARAMS); cleanup(); return rc;
-    }
     if (launch_device(d, s.s)) { cleanup(); return -1; }
 
     if (a->out_mode == MFS_OUT_FULL) {
       MFS_TRY(cudaMemcpyAsync(a->ms_out + b0 * T * M, s.ms_out, sizeof(double) * n * T * M, D2H, s.s));
       if (a->mean_out) MFS_TRY(cudaMemcpyAsync(a->mean_out + b0 * T, s.mean_out, sizeof(double) * n * T, D2H, s.s));
       if (a->scale_out) MFS_TRY(cudaMemcpyAsync(a->scale_out + b0 * T, s.scale_out, sizeof(double) * n * T, D2H, s.s));
+    } else if (a->out_mode == MFS_OUT_MEANVAR) {
+      MFS_TRY(cudaMemcpyAsync(a->ms_out + b0 * T * 2, s.ms_out, sizeof(double) * n * T * 2, D2H, s.s));
     } else if (a->out_mode == MFS_OUT_LAST) {
       MFS_TRY(cudaMemcpyAsync(a->ms_out + b0 * M, s.ms_out, sizeof(double) * n * M, D2H, s.s));
       if (a->mean_out) MFS_TRY(cudaMemcpyAsync(a->mean_out + b0, s.mean_out, sizeof(double) * n, D2H, s.s));

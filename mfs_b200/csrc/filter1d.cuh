@@ -1,5 +1,13 @@
-// The batched 1D moment filter: one filter per thread, the whole time loop inside the kernel, all per-filter state in
-// registers.  Restates the scan bodies of mfs/one_dim/filtering.py:73-86 (raw), :140-158 (central), :218-237 (scaled).
+// The batched 1D moment filter: one filter per thread, the whole time loop inside the kernel.
+// Restates the scan bodies of mfs/one_dim/filtering.py:73-86 (raw), :140-158 (central), :218-237 (scaled).
+//
+// Where the per-filter state lives (round 2): the moments and the eigen-solve (d, e, z) are in registers; the N atoms
+// (w_i, x_i) of the current quadrature -- and, per transition kind, one or two values per atom that the prediction
+// needs twice (tanh x_i, or the Normal family's (mu_i, var_i)) -- are PARKED IN SHARED MEMORY ([rows][kBlock] tile, one
+// column per thread: a warp touches 32 consecutive doubles, conflict-free).  The atoms are dead while the Hankel
+// recurrence of the next half-step runs and the prediction only streams them once per node, so keeping them in
+// registers made the 128-register build spill ~1.3 KB per thread (ncu r1 v5: 70 local loads + 40 local stores per
+// filter-step); parked, the kernel has no spills and fits 5 CTAs per SM at N = 8.
 #pragma once
 #include "models.cuh"
 
@@ -11,35 +19,47 @@ namespace mfs {
 constexpr int kBlock = MFS_BLOCK;
 
 // CTAs of 128 threads per SM that the register allocation must allow.  The step is a long dependent FP64 chain (QL
-// rotations), so resident warps are what hides the DFMA latency; measured on B200 (profiles/r1_occupancy_sweep.md):
-// N=5 fastest at 6 CTAs/SM (<=80 regs), N=8 at 4 (<=128 regs, spills beyond), N=12 at 3 (<=168 regs).
+// rotations), so resident warps are what hides the DFMA latency (profiles/r2_occupancy.md).
 #ifdef MFS_MIN_BLOCKS
 template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 #else
-template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
+template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 8 ? 5 : N <= 10 ? 4 : 3; }
 #endif
+
+// Carried filter state: [0, 2N) moments, [2N, 3N) atom weights, [3N, 4N) atom nodes, mean, scale, nell, flag.
+// flag: 1 = the atoms are the prediction quadrature of the next step, 0 = they are not (first step, stable=True, literal
+// recursion), -(1 + s) = the filter failed at (absolute) step s: everything downstream is NaN.
+// Used (a) by the segmented execution below and (b) as the public time-chunked resume state of the C ABI
+// (mfs_filter1d_args.carry_in / carry_out).
+template <int N>
+constexpr int seg_state_doubles() { return 4 * N + 4; }
 
 // Segmented execution (long horizons).  A filter that loses positive definiteness idles for the rest of the scan, and
 // a warp with one live lane costs as much as a full one; so the host cuts the time axis into segments and every
 // segment runs only the filters that are still alive, re-packed densely: at the end of a segment a live filter parks
-// its state (posterior moments, atoms, mean, scale, nell) in the workspace and appends its id to the next segment's
-// list (warp-aggregated atomic; the order of the list is irrelevant, results are per filter).  No host round-trip:
-// every launch is sized for the initial batch and threads beyond the device-side count exit at once.
+// its state in the workspace and appends its id to the next segment's list (warp-aggregated atomic; the order of the
+// list is irrelevant, results are per filter).  No host round-trip: every launch is sized for the initial batch and
+// threads beyond the device-side count exit at once.
 struct SegInfo {
   const int32_t* idx_in;    // filter ids of this segment (nullptr: identity, first segment / unsegmented)
   const int32_t* count_in;  // how many ids (nullptr: P.B)
   int32_t* idx_out;         // ids alive at the end of the segment (nullptr: last segment / unsegmented)
   int32_t* count_out;
-  double* state;            // [B][4N + 4] parked filter state
-  int64_t t0, t1;           // time steps [t0, t1)
+  const double* state_in;   // [B][4N + 4] state to resume from (nullptr: start from ms0 / mean0 / scale0)
+  double* state_out;        // [B][4N + 4] state at the end of the segment (nullptr: not kept)
+  int64_t t0, t1;           // time steps [t0, t1) of this launch, relative to P.ys / the output rows
   int32_t defer_nan_fill;   // 1: a failing filter only records its status; nan_fill_kernel writes the NaN tails
+  int32_t last;             // 1: last segment of the call (writes nell / status / LAST outputs)
 };
-
-template <int N>
-constexpr int seg_state_doubles() { return 4 * N + 4; }
 
 // Transition kinds the kernel is specialised on (compile time); drift / order / family are runtime switches inside.
 enum { KIND_TME = 0, KIND_NORMAL = 1, KIND_BENES_TME = 2 };
+
+// rows of the shared-memory tile: w, x, and what the prediction keeps per atom between its two passes
+template <int N, int MODE, int KIND>
+constexpr int smem_rows() {
+  return MODE == MFS_MODE_RAW ? 2 * N : KIND == KIND_BENES_TME ? 3 * N : KIND == KIND_NORMAL ? 4 * N : 2 * N;
+}
 
 MFS_DEV double load_y(const void* ys, int dtype, int64_t off) {
   if (dtype == MFS_YS_U8) return (double)__ldg(reinterpret_cast<const unsigned char*>(ys) + off);
@@ -64,40 +84,42 @@ MFS_DEV void times_factorials(double (&ms)[2 * N]) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Prediction: ms <- sum_i w_i T(x_i), with (mean, scale) <- predicted mean / scale in CENTRAL / SCALED modes.
+// The atoms are read from the shared-memory tile `sm` (w_i at row i, x_i at row N + i, scratch rows from 2N).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND>
-MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const double (&w)[N], const double (&x)[N],
-                     double (&ms)[2 * N], double& mean, double& scale) {
+MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, double* __restrict__ sm, double (&ms)[2 * N],
+                     double& mean, double& scale) {
   const double c = 0.5 * P.dispersion * P.dispersion;
   const double dt = P.dt;
-  double tn[N];  // Benes: tanh at the nodes, kept between the two passes
-  double mu_n[N], var_n[N];  // Normal families, central mode: (mean, var) at the nodes, kept between the two passes
+#define MFS_W(i) sm[(i) * kBlock]
+#define MFS_X(i) sm[(N + (i)) * kBlock]
+#define MFS_A(i) sm[(2 * N + (i)) * kBlock]
+#define MFS_B(i) sm[(3 * N + (i)) * kBlock]
 
   // pass 1: predicted mean (and scale) -- filtering.py:146-147, :223-224
-  if (KIND == KIND_BENES_TME) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) tn[i] = tanh_fast(x[i]);
-  }
   if (MODE != MFS_MODE_RAW) {
     double m_acc = 0.0, v_acc = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+      const double wi = MFS_W(i), xi = MFS_X(i);
       double mu, var;
       if (KIND == KIND_BENES_TME) {
         // mean = x + dt tanh x (all orders), var = dt + dt^2 (1 - tanh^2 x) (order >= 2)
-        mu = fma(dt, tn[i], x[i]);
-        var = (P.tme_order >= 2) ? fma(dt * dt, fma(-tn[i], tn[i], 1.0), dt) : dt;
+        const double tn = tanh_fast(xi);
+        MFS_A(i) = tn;
+        mu = fma(dt, tn, xi);
+        var = (P.tme_order >= 2) ? fma(dt * dt, fma(-tn, tn, 1.0), dt) : dt;
       } else if (KIND == KIND_NORMAL) {
         // (state_cond_mean of the tme_normal factory is tme.expectation(identity): the same expansion as the mean)
-        normal_mean_var(P.trans_id, P.drift_id, P.tme_order, x[i], c, dt, tprm, mu, var);
-        mu_n[i] = mu;
-        var_n[i] = var;
+        normal_mean_var(P.trans_id, P.drift_id, P.tme_order, xi, c, dt, tprm, mu, var);
+        MFS_A(i) = mu;
+        MFS_B(i) = var;
       } else {
-        const Jet j = drift_jet(P.drift_id, x[i], tprm);
-        tme_mean_var(j, x[i], c, dt, P.tme_order, mu, var);
+        const Jet j = drift_jet(P.drift_id, xi, tprm);
+        tme_mean_var(j, xi, c, dt, P.tme_order, mu, var);
       }
-      m_acc = fma(w[i], mu, m_acc);
-      v_acc = fma(w[i], var, v_acc);
+      m_acc = fma(wi, mu, m_acc);
+      v_acc = fma(wi, var, v_acc);
     }
     mean = m_acc;
     if (MODE == MFS_MODE_SCALED) scale = sqrt(v_acc);
@@ -105,9 +127,6 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
   const double sinv = (MODE == MFS_MODE_SCALED) ? 1.0 / scale : 1.0;
 
   // pass 2: moments
-#pragma unroll
-  for (int p = 0; p < 2 * N; ++p) ms[p] = 0.0;
-
   if (KIND == KIND_BENES_TME) {
     // a^2 + a' = 1 and a a' + a''/2 = 0 collapse the expansion (b = 1):  G_k = const_k (k even), const_k tanh(x) (k odd)
     double s0[2 * N], s1[2 * N];
@@ -115,12 +134,14 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
     for (int q = 0; q < 2 * N; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double delta = (MODE == MFS_MODE_RAW) ? x[i] : (x[i] - mean) * sinv;
-      const double wt = w[i] * tn[i];
+      const double wi = MFS_W(i), xi = MFS_X(i);
+      const double tn = (MODE != MFS_MODE_RAW) ? MFS_A(i) : tanh_fast(xi);
+      const double delta = (MODE == MFS_MODE_RAW) ? xi : (xi - mean) * sinv;
+      const double wt = wi * tn;
       double pw = 1.0;
 #pragma unroll
       for (int q = 0; q < 2 * N; ++q) {
-        s0[q] = fma(w[i], pw, s0[q]);
+        s0[q] = fma(wi, pw, s0[q]);
         s1[q] = fma(wt, pw, s1[q]);
         pw *= delta;
       }
@@ -139,8 +160,9 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
     const double g4 = ((o2 ? 0.125 * dt2 : 0.0) + (o3 ? 0.25 * dt3 : 0.0)) * si4;
     const double g5 = (o3 ? 0.125 * dt3 : 0.0) * si4 * sinv;                        // * tanh
     const double g6 = (o3 ? dt3 / 48.0 : 0.0) * si4 * si2;
+    // descending p: s0[p] / s1[p] are dead once ms[p] is formed, so the result grows into the registers they free
 #pragma unroll
-    for (int p = 0; p < 2 * N; ++p) {
+    for (int p = 2 * N - 1; p >= 0; --p) {
       double acc = s0[p];
       if (p >= 1) acc = fma(g1, s1[p - 1], acc);
       if (p >= 2) acc = fma(g2, s0[p - 2], acc);
@@ -152,18 +174,21 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
     }
     times_factorials<N>(ms);
   } else if (KIND == KIND_TME) {
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) ms[p] = 0.0;
     double sk[7];
     sk[0] = 1.0;
 #pragma unroll
     for (int k = 1; k < 7; ++k) sk[k] = sk[k - 1] * sinv;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const Jet j = drift_jet(P.drift_id, x[i], tprm);
+      const double wi = MFS_W(i), xi = MFS_X(i);
+      const Jet j = drift_jet(P.drift_id, xi, tprm);
       const TmeCoef cf = tme_coefficients(j, c, dt, P.tme_order);
       double wg[7];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) wg[k] = w[i] * cf.g[k] * sk[k];
-      const double delta = (MODE == MFS_MODE_RAW) ? x[i] : (x[i] - mean) * sinv;
+      for (int k = 0; k < 7; ++k) wg[k] = wi * cf.g[k] * sk[k];
+      const double delta = (MODE == MFS_MODE_RAW) ? xi : (xi - mean) * sinv;
       double pq[2 * N];
       scaled_powers<N>(delta, pq);
 #pragma unroll
@@ -178,57 +203,81 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, const doubl
     times_factorials<N>(ms);
   } else {  // KIND_NORMAL: moments of N(mu - mean, var) by M_p = mu M_{p-1} + (p-1) var M_{p-2}  (= moments.py:70-74)
 #pragma unroll
+    for (int p = 0; p < 2 * N; ++p) ms[p] = 0.0;
+    // SCALED: the reference's Normal factories return raw_moment_of_normal(mu - mean, var, p) / prod_k scale^k for EVERY
+    // order p (mfs/one_dim/moments.py:205, :243: `/ jnp.prod(scale ** orders)`, not `/ scale ** orders`), so the
+    // zeroth "moment" is scale^{-N(2N-1)} rather than 1.  Reproduced literally (bar: identical to the reference).
+    double div_all = 1.0;
+    if (MODE == MFS_MODE_SCALED) {
+      double pr = 1.0, pk = 1.0;
+#pragma unroll
+      for (int k = 1; k < 2 * N; ++k) { pk *= scale; pr *= pk; }
+      div_all = 1.0 / pr;
+    }
+#pragma unroll
     for (int i = 0; i < N; ++i) {
+      const double wi = MFS_W(i);
       double mu, var;
       if (MODE == MFS_MODE_RAW) {
-        normal_mean_var(P.trans_id, P.drift_id, P.tme_order, x[i], c, dt, tprm, mu, var);
+        normal_mean_var(P.trans_id, P.drift_id, P.tme_order, MFS_X(i), c, dt, tprm, mu, var);
       } else {   // computed by pass 1
-        mu = mu_n[i];
-        var = var_n[i];
+        mu = MFS_A(i);
+        var = MFS_B(i);
       }
       mu = (MODE == MFS_MODE_RAW) ? mu : mu - mean;
       if (var < 0.0) mu = nan("");  // variance**((p-m)/2) * 0. is NaN for every p >= 1 in the reference
       double m2 = 1.0, m1 = mu;
-      ms[0] = fma(w[i], 1.0, ms[0]);
-      ms[1] = fma(w[i], m1, ms[1]);
+      ms[0] = fma(wi, 1.0, ms[0]);
+      ms[1] = fma(wi, m1, ms[1]);
 #pragma unroll
       for (int p = 2; p < 2 * N; ++p) {
         const double mp = fma(mu, m1, (double)(p - 1) * var * m2);
-        ms[p] = fma(w[i], mp, ms[p]);
+        ms[p] = fma(wi, mp, ms[p]);
         m2 = m1;
         m1 = mp;
       }
     }
+    if (MODE == MFS_MODE_SCALED) {
+#pragma unroll
+      for (int p = 0; p < 2 * N; ++p) ms[p] *= div_all;
+    }
   }
+#undef MFS_W
+#undef MFS_X
+#undef MFS_A
+#undef MFS_B
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Update: ms <- sum_i w_i delta_i^p l_i / c ; returns c = sum_i w_i l_i   (filtering.py:82-85, :151-157, :228-236)
+// Update: ms <- sum_i w_i delta_i^p l_i / c ; returns c = sum_i w_i l_i   (filtering.py:82-85, :151-157, :228-236).
+// (w, x) arrive in registers straight from the eigen-solve; the posterior atoms {x_i, w_i l_i / c} leave through the
+// shared-memory tile (see MFS_FLAG_* in the header).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int N, int MODE>
+template <int N, int MODE, int MEAS>
 MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, double (&w)[N],
-                      const double (&x)[N], double (&ms)[2 * N], double& mean, double& scale) {
-  double u[N];
+                      const double (&x)[N], double* __restrict__ sm, double (&ms)[2 * N], double& mean, double& scale) {
   double cc = 0.0;
   MeasStep st;
   st.y = y;
-  st.c0 = (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) ? 0.0 : meas_step_constant(P.meas_id, y, mprm[1]);
+  if (MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) st.c0 = 0.0;
+  else if (MEAS == MFS_MEAS_POISSON_SOFTPLUS) st.c0 = lgamma(y + 1.0);
+  else st.c0 = (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) ? 0.0 : meas_step_constant(P.meas_id, y, mprm[1]);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    u[i] = w[i] * measurement_pdf(P.meas_id, st, x[i], mprm);
-    cc += u[i];
+    w[i] = w[i] * measurement_pdf_ct<MEAS>(P.meas_id, st, x[i], mprm);   // u_i = w_i l_i
+    cc += w[i];
   }
   const double cinv = 1.0 / cc;
   double sinv = 1.0;
   if (MODE != MFS_MODE_RAW) {
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc = fma(u[i], x[i], acc);
+    for (int i = 0; i < N; ++i) acc = fma(w[i], x[i], acc);
     mean = acc * cinv;
     if (MODE == MFS_MODE_SCALED) {
       double v = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) { const double dlt = x[i] - mean; v = fma(u[i], dlt * dlt, v); }
+      for (int i = 0; i < N; ++i) { const double dlt = x[i] - mean; v = fma(w[i], dlt * dlt, v); }
       scale = sqrt(v * cinv);
       sinv = 1.0 / scale;
     }
@@ -238,7 +287,8 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double delta = (MODE == MFS_MODE_RAW) ? x[i] : (x[i] - mean) * sinv;
-    double pw = u[i];
+    double pw = w[i];
+    sm[i * kBlock] = pw * cinv;        // posterior weight; the node stays where the eigen-solve put it
 #pragma unroll
     for (int p = 0; p < 2 * N; ++p) {
       ms[p] += pw;
@@ -247,106 +297,123 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   }
 #pragma unroll
   for (int p = 0; p < 2 * N; ++p) ms[p] *= cinv;
-  // the posterior is the N-atom measure {x_i, u_i / c}: its weights replace the prior ones (see MFS_FLAG_* in the header)
-#pragma unroll
-  for (int i = 0; i < N; ++i) w[i] = u[i] * cinv;
   return cc;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-template <int N, int MODE, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P, const SegInfo G) {
-#ifdef MFS_QL_SMEM
-  extern __shared__ double ql_smem[];                 // [3N][kBlock]: (d, e, z) of the eigen-solve, one column per thread
-  double* const ql_tile = ql_smem + threadIdx.x;
+// The eigen-solve's first-row vector z lives in the (then dead) weight rows of the shared-memory tile unless
+// MFS_Z_REGS asks for the all-register QL.
+#ifdef MFS_Z_REGS
+#define MFS_QUADRATURE(ms, mean, scale, w, x, ldl) moment_quadrature<N>(ms, mean, scale, w, x, ldl)
+#else
+#define MFS_QUADRATURE(ms, mean, scale, w, x, ldl) moment_quadrature_zs<N, kBlock>(ms, mean, scale, w, x, ldl, sm)
 #endif
+
+// (mean, variance) of the filtering distribution from the carried representation -- MFS_OUT_MEANVAR.
+template <int N, int MODE>
+MFS_DEV double2 mean_var(const double (&ms)[2 * N], double mean, double scale) {
+  if (MODE == MFS_MODE_RAW) return make_double2(ms[1], fma(-ms[1], ms[1], ms[2]));
+  if (MODE == MFS_MODE_CENTRAL) return make_double2(mean, ms[2]);
+  return make_double2(mean, scale * scale * ms[2]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N, int MODE, int KIND, int MEAS>
+__global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P, const SegInfo G) {
+  extern __shared__ double smem_tile[];                 // [smem_rows][kBlock], one column per thread
+  double* const sm = smem_tile + threadIdx.x;
   const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t n_active = G.count_in ? (int64_t)__ldg(G.count_in) : P.B;
   if (slot >= n_active) return;
   const int64_t b = G.idx_in ? (int64_t)__ldg(G.idx_in + slot) : slot;
-  const bool resume = G.t0 > 0;
-  double* park = G.state ? G.state + b * seg_state_doubles<N>() : nullptr;
+  const double* park_in = G.state_in ? G.state_in + b * seg_state_doubles<N>() : nullptr;
+  double* park_out = G.state_out ? G.state_out + b * seg_state_doubles<N>() : nullptr;
+
+  // parameter grid over shared records: filter b = row * grid_records + rec
+  const int64_t row = P.grid_records > 0 ? b / P.grid_records : b;
+  const int64_t rec = P.grid_records > 0 ? b - row * P.grid_records : b;
 
   double ms[2 * N];
   double mean, scale;
-  if (!resume) {
-    const double* ms0 = P.ms0 + b * P.ms0_stride;
+  double nell = 0.0;
+  int status = -1;
+  bool have_atoms = false;
+  if (!park_in) {
+    const double* ms0 = P.ms0 + row * P.ms0_stride;
 #pragma unroll
     for (int p = 0; p < 2 * N; ++p) ms[p] = __ldg(ms0 + p);
-    mean = (MODE != MFS_MODE_RAW) ? __ldg(P.mean0 + b * P.mean0_stride) : 0.0;
-    scale = (MODE == MFS_MODE_SCALED) ? __ldg(P.scale0 + b * P.scale0_stride) : 1.0;
+    mean = (MODE != MFS_MODE_RAW) ? __ldg(P.mean0 + row * P.mean0_stride) : 0.0;
+    scale = (MODE == MFS_MODE_SCALED) ? __ldg(P.scale0 + row * P.scale0_stride) : 1.0;
   } else {
 #pragma unroll
-    for (int p = 0; p < 2 * N; ++p) ms[p] = park[p];
-    mean = (MODE != MFS_MODE_RAW) ? park[4 * N] : 0.0;
-    scale = (MODE == MFS_MODE_SCALED) ? park[4 * N + 1] : 1.0;
+    for (int p = 0; p < 2 * N; ++p) ms[p] = park_in[p];
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) sm[i * kBlock] = park_in[2 * N + i];   // atoms: w rows, then x rows
+    mean = (MODE != MFS_MODE_RAW) ? park_in[4 * N] : 0.0;
+    scale = (MODE == MFS_MODE_SCALED) ? park_in[4 * N + 1] : 1.0;
+    nell = park_in[4 * N + 2];
+    const double flag = park_in[4 * N + 3];
+    have_atoms = flag > 0.0;
+    if (flag < 0.0) status = (int)(-flag) - 1;   // failed in an earlier chunk: NaN from the first step of this one
   }
-  const double* tprm = P.trans_params + b * P.trans_param_stride;
-  const double* mprm = P.meas_params + b * P.meas_param_stride;
+  const double* tprm = P.trans_params + row * P.trans_param_stride;
+  const double* mprm = P.meas_params + row * P.meas_param_stride;
   double tp[MFS_MAX_PARAMS], mp[MFS_MAX_PARAMS];
 #pragma unroll
   for (int k = 0; k < MFS_MAX_PARAMS; ++k) { tp[k] = __ldg(tprm + k); mp[k] = __ldg(mprm + k); }
-  if (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) mp[2] = 1.0 / mp[0];
+  if (MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC || (MEAS == kMeasRuntime && P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC))
+    mp[2] = 1.0 / mp[0];
 
-  const int64_t ys_off = b * P.ys_stride_b;
+  const int64_t ys_off = rec * P.ys_stride_b;
   double* ms_out = P.ms_out ? P.ms_out + b * P.ms_stride_b : nullptr;
   double* mean_out = P.mean_out ? P.mean_out + b * P.aux_stride_b : nullptr;
   double* scale_out = P.scale_out ? P.scale_out + b * P.aux_stride_b : nullptr;
 
-  double nell = 0.0;
-  int status = -1;
-  double w[N], x[N];          // quadrature of the current half-step; carried across steps as the posterior atoms
-  bool have_atoms = false;
-  if (resume) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) { w[i] = park[2 * N + i]; x[i] = park[3 * N + i]; }
-    nell = park[4 * N + 2];
-    have_atoms = park[4 * N + 3] != 0.0;
-  }
   int64_t t = G.t0;
-  double y_next = load_y(P.ys, P.ys_dtype, ys_off + t * P.ys_stride_t);
-  for (; t < G.t1; ++t) {
-    const double y = y_next;
-    if (t + 1 < G.t1) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
+  if (status < 0 && t < G.t1) {
+    double y_next = load_y(P.ys, P.ys_dtype, ys_off + t * P.ys_stride_t);
+    for (; t < G.t1; ++t) {
+      const double y = y_next;
+      if (t + 1 < G.t1) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
 
-    // two half-steps sharing ONE instance of the quadrature code: phase 0 = prediction, phase 1 = update.
-    // From the second step on, phase 0 re-uses the atoms (x_i, w_i l_i / c) of the previous update as its quadrature.
-    bool ok = true;
-#pragma unroll 1
-    for (int phase = 0; phase < 2; ++phase) {
-      {
-        // ONE instance of the moments -> Jacobi code; with carried atoms only its pivot test is used
+      // Half-step 1, prediction (filtering.py:78-80).  From the second step on its quadrature is known: the posterior
+      // of the previous update IS the N-atom measure parked in shared memory, so only the Hankel pivots of the
+      // posterior moments are tested (the same quantity the reference's Cholesky fails on -> NaN).  The literal
+      // recursion (first step, MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE, stable=True) derives the rule from the moments.
+      bool ok;
+      if (have_atoms) {
         double dj[N], ej[N];
-        ok = jacobi_from_moments<N, false>(ms, dj, ej);
+        ok = jacobi_from_moments<N, false>(ms, dj, ej);          // pivot test only: ej is dead code here
+      } else {
+        double w[N], x[N];
+        ok = MFS_QUADRATURE(ms, mean, scale, w, x, P.stable != 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { sm[i * kBlock] = w[i]; sm[(N + i) * kBlock] = x[i]; }
+      }
+      if (ok) {
+        predict<N, MODE, KIND>(P, tp, sm, ms, mean, scale);
+        // Half-step 2, update (filtering.py:82-86)
+        double w[N], x[N];
+        ok = MFS_QUADRATURE(ms, mean, scale, w, x, P.stable != 0);
         if (ok) {
-#ifdef MFS_QL_SMEM
-          if (!(phase == 0 && have_atoms)) ok = jacobi_to_rule_smem<N, kBlock>(dj, ej, mean, scale, w, x, ql_tile);
-#else
-          if (!(phase == 0 && have_atoms)) ok = jacobi_to_rule<N>(dj, ej, mean, scale, w, x);
-#endif
-        } else if (P.stable) {
-          // stable=True: a non-positive pivot is not a failure but the LDL completion of mfs/utils.py:526-538
-          ok = moment_quadrature_stable_fallback<N>(ms, mean, scale, w, x);
+#pragma unroll
+          for (int i = 0; i < N; ++i) sm[(N + i) * kBlock] = x[i];
+          const double cc = update<N, MODE, MEAS>(P, mp, y, w, x, sm, ms, mean, scale);
+          nell -= log(cc);
+          // stable=True always re-derives the prediction quadrature (its LDL completion is defined on the moments)
+          have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE) && !P.stable;
         }
       }
-      if (!ok) break;
-      if (phase == 0) {
-        predict<N, MODE, KIND>(P, tp, w, x, ms, mean, scale);
-      } else {
-        const double cc = update<N, MODE>(P, mp, y, w, x, ms, mean, scale);
-        nell -= log(cc);
-        // stable=True always re-derives the prediction quadrature (its LDL completion is defined on the moments)
-        have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE) && !P.stable;
-      }
-    }
-    if (!ok) { status = (int)t; break; }
+      if (!ok) { status = (int)(P.t_offset + t); break; }
 
-    if (P.out_mode == MFS_OUT_FULL) {
-      double* o = ms_out + t * P.ms_stride_t;
+      if (P.out_mode == MFS_OUT_FULL) {
+        double* o = ms_out + t * P.ms_stride_t;
 #pragma unroll
-      for (int p = 0; p < 2 * N; p += 2) *reinterpret_cast<double2*>(o + p) = make_double2(ms[p], ms[p + 1]);
-      if (MODE != MFS_MODE_RAW && mean_out) mean_out[t] = mean;
-      if (MODE == MFS_MODE_SCALED && scale_out) scale_out[t] = scale;
+        for (int p = 0; p < 2 * N; p += 2) *reinterpret_cast<double2*>(o + p) = make_double2(ms[p], ms[p + 1]);
+        if (MODE != MFS_MODE_RAW && mean_out) mean_out[t] = mean;
+        if (MODE == MFS_MODE_SCALED && scale_out) scale_out[t] = scale;
+      } else if (P.out_mode == MFS_OUT_MEANVAR) {
+        *reinterpret_cast<double2*>(ms_out + t * P.ms_stride_t) = mean_var<N, MODE>(ms, mean, scale);
+      }
     }
   }
 
@@ -358,26 +425,38 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
     for (int p = 0; p < 2 * N; ++p) ms[p] = qnan;
     mean = qnan;
     scale = qnan;
-    if (P.out_mode == MFS_OUT_FULL && !G.defer_nan_fill) {
+    if ((P.out_mode == MFS_OUT_FULL || P.out_mode == MFS_OUT_MEANVAR) && !G.defer_nan_fill) {
       for (; t < P.T; ++t) {
         double* o = ms_out + t * P.ms_stride_t;
+        if (P.out_mode == MFS_OUT_MEANVAR) {
+          *reinterpret_cast<double2*>(o) = make_double2(qnan, qnan);
+          continue;
+        }
 #pragma unroll
         for (int p = 0; p < 2 * N; p += 2) *reinterpret_cast<double2*>(o + p) = make_double2(qnan, qnan);
         if (MODE != MFS_MODE_RAW && mean_out) mean_out[t] = qnan;
         if (MODE == MFS_MODE_SCALED && scale_out) scale_out[t] = qnan;
       }
     }
+    if (P.carry_out) {   // a failed filter stays failed in the next chunk of a time-chunked run
+      double* co = P.carry_out + b * seg_state_doubles<N>();
+#pragma unroll
+      for (int p = 0; p < 4 * N + 3; ++p) co[p] = qnan;
+      co[4 * N + 3] = -(double)(status + 1);
+    }
+  } else if (park_out) {
+    // alive at the end of a segment (or of a chunk: carry_out): park the state
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) park_out[p] = ms[p];
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) park_out[2 * N + i] = sm[i * kBlock];
+    park_out[4 * N] = mean;
+    park_out[4 * N + 1] = scale;
+    park_out[4 * N + 2] = nell;
+    park_out[4 * N + 3] = have_atoms ? 1.0 : 0.0;
   }
-  if (status < 0 && G.t1 < P.T) {
-    // alive at the end of a segment: park the state and enlist for the next segment
-#pragma unroll
-    for (int p = 0; p < 2 * N; ++p) park[p] = ms[p];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { park[2 * N + i] = w[i]; park[3 * N + i] = x[i]; }
-    park[4 * N] = mean;
-    park[4 * N + 1] = scale;
-    park[4 * N + 2] = nell;
-    park[4 * N + 3] = have_atoms ? 1.0 : 0.0;
+  if (status < 0 && !G.last) {
+    // alive at the end of a segment: enlist for the next one
     const unsigned peers = __activemask();           // whichever lanes arrive together share one atomic
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
@@ -397,8 +476,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   if (P.status_out) P.status_out[b] = status;
 }
 
-// Host-side launcher for one (N, MODE, KIND); defined in filter1d_inst.cu, one translation unit per N.
+// Host-side launcher for one (N, MODE, KIND, MEAS); defined in filter1d_inst.cu, one translation unit per N.
 template <int N>
-cudaError_t launch_filter1d(const mfs_filter1d_args& a, const SegInfo& g, int kind, cudaStream_t stream);
+cudaError_t launch_filter1d(const mfs_filter1d_args& a, const SegInfo& g, int kind, int meas_ct, cudaStream_t stream);
 
 }  // namespace mfs

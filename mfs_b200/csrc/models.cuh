@@ -13,11 +13,33 @@ namespace mfs {
 
 struct Jet { double a0, a1, a2, a3, a4; };  // a, a', a'', a''', a''''
 
+// exp(x) for |x| <= 708 without libdevice's special-case branches and with the polynomial coefficients as constant-bank
+// operands of the DFMAs (libdevice's exp materialises every coefficient with two UMOVs: 22 extra issue slots per call,
+// ncu r1 v5: 70 % of the instructions of the logistic were not FP64).  k = rint(x log2 e) by the magic-number add,
+// r = x - k ln2 (two-term Cody--Waite), degree-11 polynomial (Chebyshev interpolant on |r| <= ln2/2: approximation
+// error 4e-18, tools/fit_exp_poly.py), 2^k added into the exponent field.  <= 1 ulp-class error like libm.
+static __constant__ double kExpPoly[12] = {
+    0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000011p-1, 0x1.555555555555ap-3, 0x1.555555554f0bap-5,
+    0x1.111111110f21ep-7, 0x1.6c16c1880029fp-10, 0x1.a01a01b1461c5p-13, 0x1.a01991a10d9aep-16, 0x1.71ddf56d8deb5p-19,
+    0x1.28b4101c77212p-22, 0x1.af632a0f7e2cep-26};
+
+MFS_DEV double exp_fast(double x) {   // caller guarantees |x| <= 708 (result stays a normal number)
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -0x1.62e42fefa39efp-1, x);
+  r = fma(kf, -0x1.abc9e3b39803fp-56, r);
+  double p = kExpPoly[11];
+#pragma unroll
+  for (int j = 10; j >= 0; --j) p = fma(p, r, kExpPoly[j]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // tanh through one exp and one reciprocal: 1 - 2/(1 + e^{2x}).  Absolute error ~1e-16 (relative accuracy degrades
 // only for |x| << 1, where tanh enters the transition moments multiplied by dt and added to O(1) terms).  The
-// exponent is clamped so that e^{2x} stays finite (rcp_fast(inf) would be NaN); tanh is 1 to the last bit there.
+// exponent is clamped so that e^{2x} stays a normal number; tanh is +-1 to the last bit there.
 MFS_DEV double tanh_fast(double x) {
-  return fma(-2.0, rcp_fast(1.0 + exp(fmin(2.0 * x, 708.0))), 1.0);
+  return fma(-2.0, rcp_fast(1.0 + exp_fast(fmax(fmin(2.0 * x, 708.0), -708.0))), 1.0);
 }
 
 // mfs/one_dim/ss_models.py:37 (tanh), :71 (x(1-theta1 x^2)); tests/test_filtering.py:45 (-x/ell as a*x)
@@ -161,10 +183,33 @@ static __device__ __noinline__ double measurement_pdf_generic(int meas_id, doubl
 MFS_DEV double measurement_pdf(int meas_id, const MeasStep& st, double x, const double* prm) {
   if (meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
     const double zz = fma(x * x, x * prm[2], -prm[1]);      // prm[2] = 1/c0, filled in by the kernel prologue
-    const double p = rcp_fast(1.0 + exp(fmin(-zz, 708.0)));   // 1/(1+inf) = 0 in the reference; 3e-308 here
+    const double p = rcp_fast(1.0 + exp_fast(fmax(fmin(-zz, 708.0), -708.0)));   // 1/(1+inf) = 0 in the reference; 3e-308 here
     return (st.y != 0.0) ? p : 1.0 - p;
   }
   return measurement_pdf_generic(meas_id, st.y, st.c0, x, prm[0], prm[1]);
+}
+
+// exp for any argument: the branch-free polynomial path inside |x| <= 708, libdevice outside (overflow / underflow /
+// NaN semantics of the reference).
+MFS_DEV double exp_any(double x) { return (fabs(x) <= 708.0) ? exp_fast(x) : exp(x); }
+
+// Compile-time measurement kind (MEAS = MFS_MEAS_* or -1 = the run-time switch above): the likelihood of the headline
+// models is inlined next to the node loop instead of sitting behind a run-time branch and an out-of-line call
+// (ncu r1 N=7 Normal-family capture: 26 % of the issued instructions and the instruction-fetch stalls were there).
+constexpr int kMeasRuntime = -1;
+
+template <int MEAS>
+MFS_DEV double measurement_pdf_ct(int meas_id, const MeasStep& st, double x, const double* prm) {
+  if (MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
+    return measurement_pdf(MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC, st, x, prm);
+  } else if (MEAS == MFS_MEAS_POISSON_SOFTPLUS) {
+    // poisson.pmf(y, log(1 + exp(theta2 x))) = exp(xlogy(y, mu) - lgamma(y + 1) - mu)   (ss_models.py:80-84)
+    const double mu = log(1.0 + exp_any(prm[0] * x));
+    const double klogmu = (st.y == 0.0) ? 0.0 : st.y * log(mu);
+    return exp_any(klogmu - st.c0 - mu);
+  } else {
+    return measurement_pdf(meas_id, st, x, prm);
+  }
 }
 
 template <int P>

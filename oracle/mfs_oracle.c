@@ -388,6 +388,13 @@ static void run_filter(const mfs_filter1d_args* a, int64_t b) {
         for (int p = 0; p < M; ++p) ms[p] += w[i] * raw_moment_of_normal(mp, vh, p);
       }
     }
+    if (mode == MFS_MODE_SCALED && a->trans_id != MFS_TRANS_TME) {
+      /* the reference's scaled Normal / Euler factories divide EVERY order by prod_k scale^k
+       * (mfs/one_dim/moments.py:205, :243: `/ jnp.prod(scale ** jnp.arange(num_moments))`) -- restated as is */
+      double s_all = 1.0;
+      for (int k = 0; k < M; ++k) s_all *= pow(scale, (double)k);
+      for (int p = 0; p < M; ++p) ms[p] /= s_all;
+    }
     /* update */
     if (moment_quadrature(n, ms, mean, scale, a->stable, w, x)) { status = (int)t; break; }
     double pdf_y = 0.0;

@@ -412,8 +412,32 @@ def golden_characteristic():
     print('golden_characteristic.npz')
 
 
+def golden_scaled_normal():
+    """moment_filter_scms with the reference's Normal-approximation factories, whose scaled transition moments divide
+    EVERY order by prod(scale ** arange(2N)) (mfs/one_dim/moments.py:205, 243).  The 'euler' entries are 100 % reference
+    code; 'tme_normal3' takes tme.mean_and_cov from the oracle and the reference's own factory formula around it."""
+    rng = np.random.Generator(np.random.PCG64(671))
+    n_traj = 4
+    out = {}
+    for N in (3, 5):
+        dt, T, ts, init_cond, drift, dispersion, logistic, pmf, _ = benes_bernoulli(N)
+        ys_all = synth_benes_bernoulli(rng, T, dt, n_traj)
+        out[f'N{N}/ys'], out[f'N{N}/scms0'] = ys_all, np.asarray(init_cond.scms)
+        out[f'N{N}/mean0'], out[f'N{N}/scale0'], out[f'N{N}/dt'] = float(init_cond.mean), float(np.sqrt(init_cond.variance)), dt
+        variants = {'euler': sde_cond_moments_euler(drift, dispersion, dt, N),
+                    'tme_normal3': O.sde_cond_moments_tme_normal('benes', (), 1., dt, 3, N)}
+        for vname, fam in variants.items():
+            for k in range(n_traj):
+                scmss, means, scales, nell = moment_filter_scms(fam[2], fam[4], pmf, init_cond.scms, init_cond.mean,
+                                                                jnp.sqrt(init_cond.variance), jnp.asarray(ys_all[k]))
+                out[f'N{N}/{vname}/{k}/scmss'], out[f'N{N}/{vname}/{k}/means'] = np.asarray(scmss), np.asarray(means)
+                out[f'N{N}/{vname}/{k}/scales'], out[f'N{N}/{vname}/{k}/nell'] = np.asarray(scales), float(nell)
+    np.savez_compressed(os.path.join(HERE, 'golden_filter_1d_scaled_normal.npz'), **out)
+    print('golden_filter_1d_scaled_normal.npz')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force', 'stable', 'characteristic']
+    which = sys.argv[1:] or ['quadrature', 'conversions', 'filter1d', 'multi_indices', 'nd', 'brute_force', 'stable', 'characteristic', 'scaled_normal']
     if 'multi_indices' in which:
         golden_multi_indices()
     if 'nd' in which:
@@ -430,3 +454,5 @@ if __name__ == '__main__':
         golden_conversions()
     if 'filter1d' in which:
         golden_filter_1d()
+    if 'scaled_normal' in which:
+        golden_scaled_normal()

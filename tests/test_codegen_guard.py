@@ -37,7 +37,10 @@ def test_ql_arrays_stay_in_registers(tmp_path):
         # the mailboxes are addressed with constant offsets; a register-indexed local access means an array was demoted
         dyn = [ln for ln in k.splitlines() if re.search(r'(ld|st)\.local', ln) and re.search(r'\[%rd\d+\]', ln)
                and 'depot' not in ln]
-        base_regs = set(re.findall(r'add\.u64\s+(%rd\d+), %SPL, \d+', k)) | set(re.findall(r'cvta\.local\.u64\s+(%rd\d+)', k))
+        base_regs = set(re.findall(r'add\.u64\s+(%rd\d+), %SPL, \d+', k)) | set(re.findall(r'cvta\.local\.u64\s+(%rd\d+)', k)) \
+            | set(re.findall(r'cvta\.to\.local\.u64\s+(%rd\d+)', k))   # mailbox addresses formed from %SP + constant
         dyn = [ln for ln in dyn if not any(f'[{r}]' in ln for r in base_regs)]
-        assert len(re.findall(r'ld\.local', k)) <= 6 * N, name
+        # two instances of the quadrature (first-step / literal recursion, and the per-step update), each reading its
+        # slow-path mailboxes (QL continuation 2N, LDL route 2N) back with constant offsets
+        assert len(re.findall(r'ld\.local', k)) <= 8 * N, name
         assert not dyn, (name, dyn[:3])

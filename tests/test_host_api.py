@@ -60,8 +60,14 @@ def test_argument_validation_without_gpu():
     assert L.mfs_filter_1d(ctypes.byref(a), None) != 0 and b'mode' in L.mfs_last_error()
     a.mode, a.dt, a.tme_order, a.B, a.T = 0, 0.01, 3, 4, 3
     assert L.mfs_filter_1d(ctypes.byref(a), None) != 0 and b'NULL' in L.mfs_last_error()
-    a.mode, a.trans_id = 2, _lib.TRANS['euler']
-    assert L.mfs_filter_1d(ctypes.byref(a), None) != 0 and b'scaled' in L.mfs_last_error()
+    a.out_mode = 9
+    assert L.mfs_filter_1d(ctypes.byref(a), None) != 0 and b'out_mode' in L.mfs_last_error()
+    a.out_mode, a.t_offset = _lib.OUT_MODE['meanvar'], -1
+    a.ms0 = a.trans_params = a.meas_params = a.nell_out = a.ys = a.ms_out = 8      # non-NULL, never dereferenced
+    assert L.mfs_filter_1d(ctypes.byref(a), None) != 0 and b't_offset' in L.mfs_last_error()
+    # the host-buffer entry point refuses the device-only carry before touching the GPU
+    a.t_offset, a.carry_out = 0, 8
+    assert L.mfs_filter_1d_host(ctypes.byref(a), 0, 0) != 0 and b'carry' in L.mfs_last_error()
 
 
 def test_python_callables_are_rejected():

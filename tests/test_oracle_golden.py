@@ -203,3 +203,21 @@ def test_characteristic_fn_golden():
             cf = np.array([O.characteristic_fn(z, g[f'mix{N}/{name}/ms'], float(g[f'mix{N}/{name}/mean']),
                                                float(g[f'mix{N}/{name}/scale'])) for z in zs])
             np.testing.assert_allclose(cf, g[f'mix{N}/{name}/cf'], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize('N', [3, 5])
+@pytest.mark.parametrize('variant', ['euler', 'tme_normal3'])
+def test_c_oracle_scaled_normal_factories_match_reference(N, variant):
+    """moment_filter_scms with the Normal-approximation factories: the reference divides EVERY order by
+    prod(scale ** arange(2N)) (mfs/one_dim/moments.py:205, 243); the fixture is that code, executed ('euler': 100 %)."""
+    g = np.load(os.path.join(GOLD, 'golden_filter_1d_scaled_normal.npz'))
+    dt, T, ts, ic, drift, disp, logistic, pmf, _ = benes_bernoulli(N)
+    fam = _handle_family(variant, dt, N, drift, disp)
+    ys = g[f'N{N}/ys']
+    o = C.filter_1d('scaled', fam[2], pmf, g[f'N{N}/scms0'], ys, mean0=float(g[f'N{N}/mean0']),
+                    scale0=float(g[f'N{N}/scale0']))
+    for k in range(ys.shape[0]):
+        np.testing.assert_allclose(o['scale'][k], g[f'N{N}/{variant}/{k}/scales'], rtol=1e-8)
+        np.testing.assert_allclose(o['mean'][k], g[f'N{N}/{variant}/{k}/means'], atol=1e-9)
+        np.testing.assert_allclose(o['ms'][k][:, 2:], g[f'N{N}/{variant}/{k}/scmss'][:, 2:], rtol=1e-6, atol=1e-9)
+        assert abs(o['nell'][k] - float(g[f'N{N}/{variant}/{k}/nell'])) < 1e-9 * abs(o['nell'][k])
