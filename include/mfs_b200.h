@@ -161,7 +161,7 @@ int64_t mfs_filter_1d_workspace_bytes(int32_t N, int64_t B, int64_t T);
 typedef struct mfs_filternd_args {
   int32_t abi_version;
   int32_t mode;          /* MFS_MODE_RAW | MFS_MODE_CENTRAL */
-  int32_t N;             /* 2..6 */
+  int32_t N;             /* 2..7 (one basis row per lane: N(N+1)/2 <= 32; the reference runs N = 5 and 7) */
   int32_t d;             /* must be 2 */
   int64_t B, T;
   int32_t trans_id;      /* MFS_TRANS_EULER | MFS_TRANS_TME_NORMAL | MFS_TRANS_TME (moments.py:414-479) */
@@ -272,7 +272,7 @@ int mfs_release_cached_memory(void);
 int mfs_moment_quadrature_1d(int32_t N, int64_t B, const double* ms, const double* mean, const double* scale,
                              int32_t sort_nodes, int32_t ldl, double* weights, double* nodes, void* stream);
 
-/* Batched d-dimensional moment quadrature (mfs/multi_dims/quadratures.py:120-178), d = 2, N = 2..6:
+/* Batched d-dimensional moment quadrature (mfs/multi_dims/quadratures.py:120-178), d = 2, N = 2..7:
  * ms[B][z] (graded-lex order, z = N(2N+1)) -> weights[B][S^2], nodes[B][S^2][2], S = N(N+1)/2, in the reference's
  * Cartesian order (node i*S + j = (lambda1_i, lambda2_j)).  mean / scale: [B][2] or NULL; inds: the (3, S, S) int32
  * table of gram_and_hankel_indices_graded_lexico(N, 2); ldl != 0: `ldl=True`.  Device pointers.  Failure -> NaN. */

@@ -3,7 +3,8 @@
 sub-step, row-wise Bayes update) through the C ABI ``mfs_brute_force``.
 
 Extension over the reference: ``ys`` may be ``(B, T)`` and ``init_ps`` ``(n,)`` or ``(B, n)`` -- B measurement records
-filtered on ONE shared grid ``xs`` (that is what makes the transition-density x density product a dense contraction).
+filtered on ONE shared grid ``xs`` (that is what makes the transition-density x density product a dense contraction);
+or ``xs`` ``(B, n)``: one grid per record, the call shape of ``dardel/benes_bernoulli/brute_force.py:73-76``.
 ``drift`` / ``dispersion`` / ``measurement_cond_pdf`` are functor handles (``mfs_b200.functors``); a Python callable
 raises ``TypeError`` -- there is no CPU path.
 """
@@ -44,6 +45,30 @@ def brute_force_filter(drift, dispersion, measurement_cond_pdf, init_ps, xs, ys,
         raise ValueError("history must be 'full' or 'last'")
     if any(np.ndim(p) > 0 for p in drift.params):
         raise ValueError('the grid operator is shared by the batch: drift parameters must be scalars')
+
+    xs_nd = xs.dim() if isinstance(xs, torch.Tensor) else np.ndim(xs)
+    if xs_nd == 2:
+        # One grid PER RECORD -- the reference's own experiment: every Monte-Carlo record gets the grid spanned by its
+        # moment-filter run (dardel/benes_bernoulli/brute_force.py:73-76).  The transition operator depends on the grid,
+        # so there is no shared dense contraction: each record runs the reference's call shape (one record, one grid;
+        # matrix-vector sub-steps on its L2-resident operator), enqueued back to back on the stream.  Results are the
+        # single-record results bit for bit.
+        ys_b = ys if isinstance(ys, torch.Tensor) else np.asarray(ys)
+        if ys_b.ndim != 2 or ys_b.shape[0] != xs.shape[0]:
+            raise ValueError('per-record grids xs (B, n) need ys (B, T) with the same B')
+        ip = init_ps if isinstance(init_ps, torch.Tensor) else np.asarray(init_ps, dtype=np.float64)
+        if ip.ndim != 2 or ip.shape[0] != xs.shape[0]:
+            raise ValueError('per-record grids xs (B, n) need init_ps (B, n): the initial density on each grid')
+        mp = measurement_cond_pdf.params
+        outs, nells = [], []
+        for k in range(xs.shape[0]):
+            meas_k = measurement_cond_pdf.with_params(*[(np.asarray(p).reshape(-1)[k] if np.ndim(p) > 0 else p) for p in mp])
+            r = brute_force_filter(drift, dispersion, meas_k, ip[k], xs[k], ys_b[k], dt, integration_steps, pred_method,
+                                   history, True, device)
+            outs.append(r[0])
+            nells.append(r[1])
+        out, nell = torch.stack(outs), torch.stack(nells)
+        return (out, nell) if return_nell else out
 
     if isinstance(ys, torch.Tensor) and ys.is_cuda:
         dev = ys.device

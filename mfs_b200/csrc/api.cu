@@ -646,7 +646,7 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
   if (!a) return fail("args is NULL");
   if (a->abi_version != MFS_ABI_VERSION) return fail("abi_version %d != %d", a->abi_version, MFS_ABI_VERSION);
   if (a->d != 2) return fail("only d = 2 is implemented (got d = %d)", a->d);
-  if (a->N < 2 || a->N > 6) return fail("N=%d outside [2, 6] for the 2-D filter", a->N);
+  if (a->N < 2 || a->N > 7) return fail("N=%d outside [2, 7] for the 2-D filter (one basis row per lane: N(N+1)/2 <= 32)", a->N);
   if (a->mode != MFS_MODE_RAW && a->mode != MFS_MODE_CENTRAL) return fail("2-D filter: mode must be raw or central");
   if (a->trans_id != MFS_TRANS_EULER && a->trans_id != MFS_TRANS_TME_NORMAL && a->trans_id != MFS_TRANS_TME)
     return fail("2-D filter: transition must be euler, tme_normal or tme (Lotka--Volterra)");
@@ -675,6 +675,7 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
     case 4: e = launch_filter_nd<4>(k, s); break;
     case 5: e = launch_filter_nd<5>(k, s); break;
     case 6: e = launch_filter_nd<6>(k, s); break;
+    case 7: e = launch_filter_nd<7>(k, s); break;
   }
   if (e != cudaSuccess) return fail("2-D filter launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -684,7 +685,7 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
 int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, const double* mean, const double* scale,
                              const int32_t* inds, int32_t ldl, double* weights, double* nodes, void* stream) {
   if (d != 2) return fail("only d = 2 is implemented (got d = %d)", d);
-  if (N < 2 || N > 6) return fail("N=%d outside [2, 6] for the 2-D quadrature", N);
+  if (N < 2 || N > 7) return fail("N=%d outside [2, 7] for the 2-D quadrature", N);
   if (B < 0) return fail("negative B");
   if (B == 0) return 0;
   if (!ms || !inds || !weights || !nodes) return fail("NULL pointer argument");
@@ -698,6 +699,7 @@ int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, 
     case 4: e = launch_quadrature_nd<4>(q, s); break;
     case 5: e = launch_quadrature_nd<5>(q, s); break;
     case 6: e = launch_quadrature_nd<6>(q, s); break;
+    case 7: e = launch_quadrature_nd<7>(q, s); break;
   }
   if (e != cudaSuccess) return fail("2-D quadrature launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

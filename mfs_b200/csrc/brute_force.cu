@@ -175,11 +175,13 @@ template <int BT>
 static cudaError_t launch_gemv(const double* A, const double* Pw, double* D, int64_t M, int n, int Kpad, int64_t b0,
                                int sms, cudaStream_t s) {
   const size_t smem = sizeof(double) * BT * Kpad;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};      // the opt-in is per device: tracked per device ordinal
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(bf_gemv_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int rows_per_cta = BF_GEMV_THREADS / 32;
   int grid = (n + rows_per_cta - 1) / rows_per_cta;
@@ -426,12 +428,14 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   } while (0)
 
   const bool chapman = a->pred_method != MFS_BF_KOLMOGOROV;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};      // the opt-in is per device: tracked per device ordinal
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess) return fail("cudaGetDevice failed");
+  if (cur_dev < 0 || cur_dev >= 64 || !configured[cur_dev]) {
     cudaError_t e = cudaFuncSetAttribute(bf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bf_kolmogorov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    configured = true;
+    if (cur_dev >= 0 && cur_dev < 64) configured[cur_dev] = true;
   }
   if (chapman) {
     const int trans = a->pred_method == MFS_BF_CHAPMAN_EULER ? MFS_TRANS_EULER : MFS_TRANS_TME_NORMAL;

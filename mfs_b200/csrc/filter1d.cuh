@@ -7,7 +7,7 @@
 // column per thread: a warp touches 32 consecutive doubles, conflict-free).  The atoms are dead while the Hankel
 // recurrence of the next half-step runs and the prediction only streams them once per node, so keeping them in
 // registers made the 128-register build spill ~1.3 KB per thread (ncu r1 v5: 70 local loads + 40 local stores per
-// filter-step); parked, the kernel has no spills and fits 5 CTAs per SM at N = 8.
+// filter-step); parked, the hot loop of the 128-register build is down to ~40 spill instructions per step.
 #pragma once
 #include "models.cuh"
 
@@ -23,7 +23,7 @@ constexpr int kBlock = MFS_BLOCK;
 #ifdef MFS_MIN_BLOCKS
 template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 #else
-template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 8 ? 5 : N <= 10 ? 4 : 3; }
+template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
 #endif
 
 // Carried filter state: [0, 2N) moments, [2N, 3N) atom weights, [3N, 4N) atom nodes, mean, scale, nell, flag.
@@ -300,12 +300,13 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   return cc;
 }
 
-// The eigen-solve's first-row vector z lives in the (then dead) weight rows of the shared-memory tile unless
-// MFS_Z_REGS asks for the all-register QL.
-#ifdef MFS_Z_REGS
-#define MFS_QUADRATURE(ms, mean, scale, w, x, ldl) moment_quadrature<N>(ms, mean, scale, w, x, ldl)
-#else
+// The eigen-solve keeps (d, e, z) in registers.  -DMFS_Z_SMEM moves its first-row vector z to the (then dead) weight
+// rows of the shared-memory tile (16 registers fewer at N = 8); measured slower on B200 at every occupancy
+// (profiles/r2_ab_1d_kernel.md: N = 8, T = 100: 2.86e9 vs 3.01e9 filter-steps/s), kept as a build option.
+#ifdef MFS_Z_SMEM
 #define MFS_QUADRATURE(ms, mean, scale, w, x, ldl) moment_quadrature_zs<N, kBlock>(ms, mean, scale, w, x, ldl, sm)
+#else
+#define MFS_QUADRATURE(ms, mean, scale, w, x, ldl) moment_quadrature<N>(ms, mean, scale, w, x, ldl)
 #endif
 
 // (mean, variance) of the filtering distribution from the carried representation -- MFS_OUT_MEANVAR.

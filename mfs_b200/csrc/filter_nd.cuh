@@ -555,7 +555,7 @@ MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scra
 #ifdef MFS_ND_MIN_BLOCKS
 template <int N> constexpr int nd_min_blocks() { return MFS_ND_MIN_BLOCKS; }
 #else
-template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N == 5 ? 3 : 2; }
+template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N == 5 ? 3 : N == 6 ? 2 : 1; }
 #endif
 template <int N>
 __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {

@@ -76,7 +76,8 @@ MFS_DEV int mixture_component(double u, const double* weights, int K) {
   return k;
 }
 
-// y ~ p(. | x) from the measurement draw.  Bernoulli: ua < p.  Poisson: inversion by sequential search on ua.
+// y ~ p(. | x) from the measurement draw.  Bernoulli: ua < p.  Poisson: inversion by sequential search on ua for rates
+// up to 64, Normal approximation beyond.
 // Gaussian: h x + r z0.
 MFS_DEV double measure(int meas_id, const double* mp, double x, const Draw& d) {
   if (meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) {
@@ -85,9 +86,17 @@ MFS_DEV double measure(int meas_id, const double* mp, double x, const Draw& d) {
   }
   if (meas_id == MFS_MEAS_POISSON_SOFTPLUS) {
     const double lam = log(1.0 + exp(mp[0] * x));
+    if (!(lam <= 64.0)) {
+      // large rates: exp(-lam) underflows for lam > 745 and the sequential search would run its full bound with the
+      // warp waiting; the Normal approximation with continuity correction, floor(lam + sqrt(lam) z + 1/2), is within
+      // O(lam^-1/2) of the Poisson law (jax.random.poisson switches to a rejection sampler there)
+      double z0, z1;
+      normals(d, z0, z1);
+      return fmax(0.0, floor(fma(sqrt(lam), z0, lam) + 0.5));     // NaN rate -> NaN measurement
+    }
     double p = exp(-lam), F = p;
     int k = 0;
-    while (d.ua > F && k < 100000) {
+    while (d.ua > F && k < 1000) {
       ++k;
       p *= lam / (double)k;
       F += p;

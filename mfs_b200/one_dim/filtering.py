@@ -160,10 +160,16 @@ def _run(mode: str, spec, meas: MeasurementFunctor, ms0, mean0, scale0, ys, stab
     if on_device:
         import torch
         dev = ys.device
-        ys_c = ys.reshape(grid_records if grid_records else B, T)
-        if ys_c.dtype == torch.bool:
-            ys_c = ys_c.view(torch.uint8)
-        ys_c = ys_c.contiguous()
+        if ys.dim() == 2 and not ys.is_contiguous() and min(ys.stride()) > 0 and ys.dtype != torch.bool:
+            # a strided 2-D view (e.g. the transpose of a time-major (T, B) buffer) is read in place through the ABI's
+            # element strides: with stride_b = 1 consecutive lanes read consecutive measurements
+            ys_c = ys
+            a.ys_stride_b, a.ys_stride_t = int(ys.stride(0)), int(ys.stride(1))
+        else:
+            ys_c = ys.reshape(grid_records if grid_records else B, T)
+            if ys_c.dtype == torch.bool:
+                ys_c = ys_c.view(torch.uint8)
+            ys_c = ys_c.contiguous()
         a.ys_dtype = _ys_dtype_code(str(ys_c.dtype))
         keep = [ys_c]
 

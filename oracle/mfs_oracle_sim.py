@@ -69,16 +69,23 @@ def measure(meas, mp, x, ua, ub):
             p = 1.0 / (1.0 + np.exp(-(x ** 3 / mp[0] - mp[1])))
         return (ua < p).astype(np.float64)
     if meas == 'poisson_softplus':
-        lam = np.log(1.0 + np.exp(mp[0] * x))
-        p = np.exp(-lam)
+        with np.errstate(over='ignore'):
+            lam = np.log(1.0 + np.exp(mp[0] * x))
+        big = ~(lam <= 64.0)                   # Normal approximation with continuity correction for large rates
+        lam_s = np.where(big, 1.0, lam)
+        p = np.exp(-lam_s)
         F = p.copy()
         k = np.zeros(x.shape)
-        live = ua > F
+        live = (ua > F) & ~big
         while live.any():
             k[live] += 1
-            p[live] *= lam[live] / k[live]
+            p[live] *= lam_s[live] / k[live]
             F[live] += p[live]
             live = live & (ua > F)
+        if big.any():
+            z0 = normals(ua, ub)[0]
+            with np.errstate(invalid='ignore'):
+                k = np.where(big, np.maximum(0.0, np.floor(lam + np.sqrt(lam) * z0 + 0.5)), k)
         return k
     if meas == 'gaussian':
         return mp[0] * x + mp[1] * normals(ua, ub)[0]

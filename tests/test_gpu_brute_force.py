@@ -139,3 +139,27 @@ def test_rejects_python_callables_and_bad_methods():
     with pytest.raises(NotImplementedError):
         brute_force_filter(benes_drift(), 1., bernoulli_logistic_cubic(), xs, xs, np.zeros(3, np.uint8), 1e-2,
                            pred_method='magic')
+
+
+def test_per_record_grids_like_the_reference_experiment():
+    """dardel/benes_bernoulli/brute_force.py:73-76: every record is filtered on its OWN grid (spanned by its moment-filter
+    run).  xs (B, n): equals the single-record calls bit for bit and the NumPy oracle on each record's grid."""
+    rng = np.random.default_rng(5)
+    B, T, n = 5, 8, 300
+    dt = 1e-2
+    _, _, ic, logistic, pmf_o = O.benes_bernoulli(5)
+    ys = (rng.random((B, T)) < 0.5).astype(np.uint8)
+    lb, ub = -3. - rng.random(B), 3. + rng.random(B)
+    xs = np.stack([np.linspace(lb[k], ub[k], n) for k in range(B)])
+    ip = np.stack([ic.pdf(xs[k]) for k in range(B)])
+    out, nell = brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip, xs, ys, dt,
+                                   integration_steps=7, pred_method='chapman-tme-3', return_nell=True)
+    assert out.shape == (B, T, n) and nell.shape == (B,)
+    for k in range(B):
+        one = brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip[k], xs[k], ys[k], dt,
+                                 integration_steps=7, pred_method='chapman-tme-3')
+        assert torch.equal(one, out[k])
+        ref = BF.brute_force_filter('benes', (), 1., pmf_o, ip[k], xs[k], ys[k], dt, 7, 'chapman-tme-3')
+        _close(out[k], ref)
+    with pytest.raises(ValueError):
+        brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip[0], xs, ys, dt)

@@ -187,3 +187,37 @@ def test_moment_quadrature_nd_against_reference_golden():
     assert np.isfinite(w).all() and np.isfinite(x).all()
     np.testing.assert_allclose(np.abs(x).max(), np.abs(s['nd/N3/x']).max(), rtol=1e-6)
     assert np.isnan(moment_quadrature_nd(s['nd/N3/ms'], gram_and_hankel_indices_graded_lexico(3, 2))[0]).all()
+
+
+def test_paper_setting_N7_against_oracle():
+    """N = 7 (z = 105 moments, s = 28 basis functions, 784 nodes): the second order the reference's prey--predator
+    experiment runs (reproduce_paper_plots/plot_prey_predator_errs.py:10; on a GPU through XLA,
+    dardel/run_prey_predator_mf_gpu.sh).  Round 1 stopped at N = 6."""
+    N, B, T = 7, 3, 5
+    mis = generate_graded_lexico_multi_indices(2, 2 * N - 1, 0)
+    inds = gram_and_hankel_indices_graded_lexico(N, 2)
+    dt, _, ts, gs, drift, dispersion, emission, pmf, simulate = prey_predator(mis)
+    rng = np.random.Generator(np.random.PCG64(679))
+    _, xs, ys = simulate(rng, integration_steps=10, T=T, n=B)
+    fam = sde_cond_moments_tme_normal(drift, dispersion, dt, 2, mis)
+    cmss, means, nell, status = moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, torch.from_numpy(ys).cuda(),
+                                                     (mis, inds), gs.cms, gs.mean, return_status=True)
+    assert cmss.shape == (B, T, 105) and means.shape == (B, T, 2)
+    status = status.cpu().numpy()
+    f_r, f_c, f_m = ND.lv_cond_moments('tme_normal', mis, order=2, use_kan=False)
+    n_ok = 0
+    for k in range(B):
+        ref_c, ref_m, ref_n = ND.moment_filter_nd_cms(f_c, f_m, ND.lv_measurement_pmf, ys[k], (mis, inds), gs.cms, gs.mean)
+        if not np.isfinite(ref_n) or status[k] >= 0:      # cond(G) ~ 1e30 at order 13: either side may lose a pivot
+            continue
+        n_ok += 1
+        np.testing.assert_allclose(means[k].cpu().numpy(), ref_m, rtol=1e-8)
+        np.testing.assert_allclose(nell[k].item(), ref_n, rtol=1e-8)
+    assert n_ok >= 1
+    # the quadrature on its own: moments of the initial Gaussian mixture are reproduced by the 784-node rule
+    from mfs_b200.multi_dims.quadratures import moment_quadrature_nd
+    w, x = moment_quadrature_nd(gs.cms, inds, mean=gs.mean)
+    assert abs(w.sum() - 1.) < 1e-9
+    d = x - gs.mean
+    lowest = [(w * d[:, 0] ** a * d[:, 1] ** b).sum() for a, b in mis[:6]]
+    np.testing.assert_allclose(lowest, gs.cms[:6], atol=1e-9)

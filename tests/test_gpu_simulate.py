@@ -156,3 +156,23 @@ def test_edge_shapes():
         _, _, y1 = simulate_1d(drift, disp, dt, T_, ic, pmf, 33, 2, scheme='benes_exact')
         r = S.simulate_1d('benes', (), 1., dt, T_, *IC, 'bernoulli_logistic_cubic', (5., 0.), 33, 2, scheme='benes_exact')
         assert np.array_equal(y1.cpu().numpy().astype(np.float64), r[2])
+
+
+def test_poisson_sampler_large_rates():
+    """Rates beyond the inversion range: theta2 x of a few hundred made exp(-lam) underflow and the sequential search
+    run its full bound with the warp waiting (round-1 advisor finding).  Large rates take the Normal approximation with
+    continuity correction; the draws equal the oracle's on the same Philox stream and have mean ~ lam, variance ~ lam."""
+    B, T = 4096, 4
+    dt, _, _, ic, drift, disp, _, pmf, _ = well_poisson(3., 5)
+    theta2 = 2000.                                       # x ~ +-0.5  ->  lam ~ 1000 on the positive side
+    dev = simulate_1d(drift(3.), disp, dt, T, ic, pmf(theta2), B, 17, integration_steps=5, return_xs=True)
+    ref = S.simulate_1d('well', (3.,), 1., dt, T, *IC, 'poisson_softplus', (theta2,), B, 17, integration_steps=5)
+    xs, ys = dev[1].cpu().numpy(), dev[2].cpu().numpy().astype(np.float64)
+    big = theta2 * ref[1] > 200.
+    assert big.sum() > 1000
+    # the rate is theta2 * x to 1e-80 there; states agree to 1e-10, so lam to ~2e-7 and the rounded draw almost always
+    assert np.mean(ys[big] == ref[2][big]) > 0.999
+    lam = theta2 * xs[big]
+    resid = (ys[big] - lam) / np.sqrt(lam)
+    assert abs(resid.mean()) < 0.1 and abs(resid.var() - 1.) < 0.15
+    assert np.all(ys[theta2 * ref[1] < -50.] == 0.)
