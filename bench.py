@@ -7,17 +7,22 @@ GPU (BASELINE.json configs[1]); metric = filter-steps/s (batch x T / time), fp64
         bench.py --gpus 8 --steps 3 --warmup 3
     python bench.py --impl reference --steps 2 --warmup 1       # CPU arm: the C restatement of the reference algorithm
 
-One "step" = one pass of the filter over the whole batch (B x T filter-steps, one kernel launch per GPU).
+One "step" = one pass of the filter over the whole batch (B x T filter-steps; T = 1000 runs as 16 segment launches with
+live-filter compaction + one NaN-tail launch per GPU).
   value   inputs (ys uint8, 1 GB) resident in HBM, full moment history (B, T, 16) written to HBM, CUDA events on the
           launching stream, barrier + synchronize on both sides, max over ranks.  ys (1 GB) > L2 (126 MB).
   e2e     the public API `moment_filter_rms(...)` with HOST buffers (pinned), H2D of ys, kernel, D2H of the full
-          history inside the timed region, on an --e2e-batch slice of the same workload (the 128 GB/step history of
-          the full batch does not fit pinned host memory); plus `e2e_nell_only` on the full batch.
-  roofline  FP64 FMA pipe (the path is compute-bound: ~53 flop/B): algorithmic flops W(8)=6851 per filter-step
-           / kernel time, against the FP64 FMA peak measured live by mfs_fp64_peak (MEASURED_PEAKS.json
+          history inside the timed region, weak-scaled (fixed filters per GPU); `e2e_modes` reports the same call for the
+          three output modes full / meanvar (mean, variance per step) / none (nell only).
+  roofline  FP64 FMA pipe (the path is compute-bound: ~53 flop/B): algorithmic flops W(8) per filter-step
+          x LIVE filter-steps / kernel time, against the FP64 FMA peak measured live by mfs_fp64_peak (MEASURED_PEAKS.json
           holds no FP64 figure).  `hbm` sub-object gives the secondary HBM figure against MEASURED_PEAKS.json.
+  secondary  the other BASELINE configurations at their stated sizes, sharded over the ranks (1/8 of the stated size per
+          rank): theta grid + argmin over NCCL (configs[3]), 2-D prey--predator filter and brute-force grid filter
+          (configs[4]); on one GPU also the data simulator and the nell + gradient kernel.
   cpu_baseline  oracle/libmfs_oracle.so (C restatement of the reference's dense algorithm, pthreads over filters) on a
-          bounded sample, all host cores.  The JAX reference itself cannot run here (no jax / tme, no network).
+          bounded sample, all host cores; `cpu_baseline_torch`: the same algorithm as batched torch-CPU linalg calls
+          (baseline/torch_cpu_filter.py).  The JAX reference itself cannot run here (no jax / tme, no network).
 """
 import argparse
 import json
@@ -138,7 +143,7 @@ def secondary_legs(rank, world, device_index, fp64_peak, scale=1.0, single_gpu_e
     import torch
     import torch.distributed as dist
     from mfs_b200 import _lib
-    from mfs_b200.parallel import shard_bounds, local_argmin, argmin_over_shards, gather_filters
+    from mfs_b200.parallel import shard_bounds, local_argmin, running_argmin, argmin_over_shards, gather_filters
     out = {}
     dev = torch.device('cuda', device_index)
 
@@ -181,21 +186,17 @@ def secondary_legs(rank, world, device_index, fp64_peak, scale=1.0, single_gpu_e
     chunk = max(1024, (1 << 23) // n_traj)          # ~8M filters per call
 
     def theta_pass(lo_, hi_, keep_cols=0):
-        best_v = torch.full((n_traj,), float('inf'), dtype=torch.float64, device=dev)
-        best_a = torch.zeros((n_traj,), dtype=torch.int64, device=dev)
-        kept, bad = [], 0.
+        best, kept, bad = None, [], 0.
         for c0 in range(lo_, hi_, chunk):
             c1 = min(hi_, c0 + chunk)
             fam = tme_normal_1d(driftw(th1[c0:c1, None]), dispw, dtw, 2, Ng)
             _, _, nell, st = moment_filter_cms(fam[1], fam[3], pmfw(th2[c0:c1, None]), icw.cms, icw.mean, ysw,
                                                history='none', return_status=True)
-            v, a = local_argmin(nell, theta_offset=c0)
-            upd = v < best_v
-            best_v, best_a = torch.where(upd, v, best_v), torch.where(upd, a, best_a)
+            best = running_argmin(best, nell, theta_offset=c0)
             bad += float((st >= 0).sum())
             if keep_cols:
                 kept.append(nell[:, :keep_cols].clone())
-        v, a = argmin_over_shards(best_v, best_a)
+        v, a = argmin_over_shards(*best)
         return v, a, bad, (torch.cat(kept) if keep_cols else None)
 
     ms, (val, arg, bad, _) = timed(lambda: theta_pass(lo, hi), warm=lambda: theta_pass(lo, min(hi, lo + chunk)))
@@ -553,7 +554,11 @@ def main():
         # full history: 16.8 GB of pinned host memory per 131072 filters and per rank
         Be_full = min(B, args.e2e_batch if world <= 2 else max(32768, args.e2e_batch // 4))
         e2e_modes['full'] = e2e_leg('full', Be_full)
-        e2e_modes['meanvar'] = e2e_leg('meanvar', min(B, 2 * args.e2e_batch), chunk=148 * 2 * 128)
+        try:       # 8.4 GB of pinned host memory per rank; half of it if the host refuses
+            e2e_modes['meanvar'] = e2e_leg('meanvar', min(B, 4 * args.e2e_batch), chunk=148 * 4 * 128)   # one full wave per chunk
+        except RuntimeError:
+            torch.cuda.empty_cache()
+            e2e_modes['meanvar'] = e2e_leg('meanvar', min(B, 2 * args.e2e_batch), chunk=148 * 4 * 128)
         e2e_modes['none'] = e2e_leg('none', B)
         e2e = dict(e2e_modes['full'])
         e2e['note'] = ('pinned host buffers, chunked H2D->kernel->D2H pipeline inside mfs_filter_1d_host; the full moment '

@@ -343,6 +343,11 @@ typedef struct mfs_simulate_lv_args {
  * mfs/multi_dims/ss_models.py:76-93. */
 int mfs_simulate_lv(const mfs_simulate_lv_args* a, void* stream);
 
+/* Diagnostic: the kernels' own elementary functions (branch-free exp / log / tanh with constant-bank polynomial
+ * coefficients, mfs_b200/csrc/models.cuh) evaluated on x[0..n); any output pointer may be NULL.  Device pointers.
+ * Used by the parity tests to bound their error against libm. */
+int mfs_math_selftest(int64_t n, const double* x, double* out_exp, double* out_log, double* out_tanh, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process since load (all threads). */
 int64_t mfs_launch_count(void);
 

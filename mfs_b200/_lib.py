@@ -124,7 +124,7 @@ class SimulateLvArgs(ctypes.Structure):
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
            'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd',
-           'mfs_simulate_1d', 'mfs_simulate_lv', 'mfs_filter_1d_grad')
+           'mfs_simulate_1d', 'mfs_simulate_lv', 'mfs_filter_1d_grad', 'mfs_math_selftest')
 
 _lib = None
 _lock = threading.Lock()
@@ -194,6 +194,8 @@ def lib() -> ctypes.CDLL:
         L.mfs_simulate_1d.restype = ctypes.c_int
         L.mfs_simulate_lv.argtypes = [ctypes.POINTER(SimulateLvArgs), ctypes.c_void_p]
         L.mfs_simulate_lv.restype = ctypes.c_int
+        L.mfs_math_selftest.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 5
+        L.mfs_math_selftest.restype = ctypes.c_int
         L.mfs_launch_count.restype = ctypes.c_int64
         L.mfs_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]

@@ -103,8 +103,10 @@ static int validate(const mfs_filter1d_args* a) {
   if (a->T > 0 && !a->ys) return fail("ys is NULL");
   if (a->mode != MFS_MODE_RAW && !a->mean0) return fail("mean0 is NULL in central/scaled mode");
   if (a->mode == MFS_MODE_SCALED && !a->scale0) return fail("scale0 is NULL in scaled mode");
-  if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
-  const bool aux = a->out_mode == MFS_OUT_FULL || a->out_mode == MFS_OUT_LAST;
+  // per-step histories are empty when T == 0: only the LAST outputs (one row per filter) are required then
+  const bool need_ms = a->out_mode == MFS_OUT_LAST || ((a->out_mode == MFS_OUT_FULL || a->out_mode == MFS_OUT_MEANVAR) && a->T > 0);
+  if (need_ms && !a->ms_out) return fail("ms_out is NULL");
+  const bool aux = a->out_mode == MFS_OUT_LAST || (a->out_mode == MFS_OUT_FULL && a->T > 0);
   if (aux && a->mode != MFS_MODE_RAW && !a->mean_out) return fail("mean_out is NULL in central/scaled mode");
   if (aux && a->mode == MFS_MODE_SCALED && !a->scale_out) return fail("scale_out is NULL in scaled mode");
   if (a->t_offset < 0) return fail("negative t_offset");
@@ -370,6 +372,17 @@ static cudaError_t launch_characteristic(int64_t B, int64_t m, const double* ms,
                                          const double* zs, double* out, cudaStream_t s) {
   characteristic_kernel<N><<<(unsigned)B, kBlock, 0, s>>>(m, ms, mean, scale, zs, out);
   return cudaGetLastError();
+}
+
+// The branch-free elementary functions of models.cuh on an array (diagnostic entry point for the parity tests).
+__global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out_exp,
+                                                            double* __restrict__ out_log, double* __restrict__ out_tanh) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  if (out_exp) out_exp[i] = exp_any(v);
+  if (out_log) out_log[i] = log_fast(v);
+  if (out_tanh) out_tanh[i] = tanh_fast(v);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -702,6 +715,17 @@ int mfs_moment_quadrature_nd(int32_t N, int32_t d, int64_t B, const double* ms, 
     case 7: e = launch_quadrature_nd<7>(q, s); break;
   }
   if (e != cudaSuccess) return fail("2-D quadrature launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mfs_math_selftest(int64_t n, const double* x, double* out_exp, double* out_log, double* out_tanh, void* stream) {
+  if (n < 0) return fail("negative n");
+  if (n == 0) return 0;
+  if (!x) return fail("x is NULL");
+  math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, x, out_exp, out_log, out_tanh);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("math selftest launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

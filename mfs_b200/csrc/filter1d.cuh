@@ -26,9 +26,11 @@ template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
 #endif
 
-// Carried filter state: [0, 2N) moments, [2N, 3N) atom weights, [3N, 4N) atom nodes, mean, scale, nell, flag.
-// flag: 1 = the atoms are the prediction quadrature of the next step, 0 = they are not (first step, stable=True, literal
-// recursion), -(1 + s) = the filter failed at (absolute) step s: everything downstream is NaN.
+// Carried filter state: [0, 2N) moments, [2N, 4N) what the next prediction starts from, mean, scale, nell, flag.
+// flag: 0 = the moments alone (first step, stable=True, literal recursion); 1 = [2N, 3N) atom weights, [3N, 4N) atom nodes
+// of the posterior, which are the prediction quadrature of the next step; 2 = [2N, 4N) the tanh-weighted power sums of
+// the posterior atoms (raw moments + Benes TME, see fuses_update_and_predict); -(1 + s) = the filter failed at (absolute)
+// step s: everything downstream is NaN.
 // Used (a) by the segmented execution below and (b) as the public time-chunked resume state of the C ABI
 // (mfs_filter1d_args.carry_in / carry_out).
 template <int N>
@@ -58,7 +60,31 @@ enum { KIND_TME = 0, KIND_NORMAL = 1, KIND_BENES_TME = 2 };
 // rows of the shared-memory tile: w, x, and what the prediction keeps per atom between its two passes
 template <int N, int MODE, int KIND>
 constexpr int smem_rows() {
+#ifdef MFS_FUSE_RAW_BENES
+  if (MODE == MFS_MODE_RAW && KIND == KIND_BENES_TME) return 4 * N;      // atoms + the parked power sums s1
+#endif
   return MODE == MFS_MODE_RAW ? 2 * N : KIND == KIND_BENES_TME ? 3 * N : KIND == KIND_NORMAL ? 4 * N : 2 * N;
+}
+
+// Raw moments + Benes TME (the headline model): the prediction of step t+1 only needs the two power-sum families
+// s0[q] = sum_i w_i x_i^q and s1[q] = sum_i w_i tanh(x_i) x_i^q over the posterior atoms of step t -- and s0 IS the
+// posterior moment vector the update of step t has just formed.  The update therefore also accumulates s1 while it has
+// the powers x_i^q in hand (one more FMA per node and order), and the next prediction is the 7-term TME combination of
+// (ms, s1): no pass over the atoms, no power table, 2N x N FMAs + N x 2N multiplies fewer per step, and the atoms never
+// leave the update.  (Raw mode only: in the central / scaled modes the powers are taken about the PREDICTED mean.)
+//
+// Measured on B200 (same-box A/B, profiles/r2_ab_1d_fusion.log): N = 8, T = 100: 3.071e9 vs 3.052e9 filter-steps/s (+0.6 %),
+// T = 1000 full history: 4.154e9 vs 4.203e9 (-1.2 %) -- neutral: the step time is set by the dependent-issue latency of the
+// QL chase, not by the number of FP64 instructions outside it.  The fusion also changes the rounding of the default path
+// (sum_i u_i x^q scaled by 1/c instead of sum_i (u_i / c) x^q), so it is an opt-in build (-DMFS_FUSE_RAW_BENES); the
+// GPU test-suite passes with it.
+template <int MODE, int KIND>
+constexpr bool fuses_update_and_predict() {
+#ifdef MFS_FUSE_RAW_BENES
+  return MODE == MFS_MODE_RAW && KIND == KIND_BENES_TME;
+#else
+  return false;
+#endif
 }
 
 MFS_DEV double load_y(const void* ys, int dtype, int64_t off) {
@@ -260,7 +286,7 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   MeasStep st;
   st.y = y;
   if (MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) st.c0 = 0.0;
-  else if (MEAS == MFS_MEAS_POISSON_SOFTPLUS) st.c0 = lgamma(y + 1.0);
+  else if (MEAS == MFS_MEAS_POISSON_SOFTPLUS) st.c0 = log_factorial(y);
   else st.c0 = (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) ? 0.0 : meas_step_constant(P.meas_id, y, mprm[1]);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -300,6 +326,85 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   return cc;
 }
 
+// Fused update (see fuses_update_and_predict): posterior raw moments AND the tanh-weighted power sums of the posterior
+// atoms.  (u_i, x_i) are parked in rows [0, 2N) and streamed back, so that only the 4N accumulators live in registers;
+// s1 leaves through rows [2N, 4N).  Returns c = sum_i w_i l_i.
+template <int N, int MEAS>
+MFS_DEV double update_fused_raw_benes(const mfs_filter1d_args& P, const double* mprm, double y, double (&w)[N],
+                                      const double (&x)[N], double* __restrict__ sm, double (&ms)[2 * N]) {
+  static_assert(MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC, "the Benes TME kind is instantiated with the Bernoulli likelihood");
+  double cc = 0.0;
+  MeasStep st;
+  st.y = y;
+  st.c0 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double u = w[i] * measurement_pdf_ct<MEAS>(P.meas_id, st, x[i], mprm);
+    sm[i * kBlock] = u;
+    sm[(N + i) * kBlock] = x[i];
+    cc += u;
+  }
+  const double cinv = 1.0 / cc;
+  double s1[2 * N];
+#pragma unroll
+  for (int p = 0; p < 2 * N; ++p) { ms[p] = 0.0; s1[p] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double xi = sm[(N + i) * kBlock];
+    const double tn = tanh_fast(xi);
+    double pw = sm[i * kBlock];
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) {
+      ms[p] += pw;
+      s1[p] = fma(pw, tn, s1[p]);
+      pw *= xi;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 2 * N; ++p) {
+    ms[p] *= cinv;
+    sm[(2 * N + p) * kBlock] = s1[p] * cinv;
+  }
+  return cc;
+}
+
+// Fused prediction: ms <- TME combination of the posterior moments (= s0) and the parked s1 (rows [2N, 4N)).
+template <int N>
+MFS_DEV void predict_fused_raw_benes(const mfs_filter1d_args& P, const double* __restrict__ sm, double (&ms)[2 * N]) {
+  const double dt = P.dt;
+  double s0[2 * N], s1[2 * N];
+  {
+    double rf = 1.0;
+#pragma unroll
+    for (int q = 0; q < 2 * N; ++q) {
+      if (q >= 2) rf *= 1.0 / q;
+      s0[q] = (q >= 2) ? ms[q] * rf : ms[q];
+      const double v = sm[(2 * N + q) * kBlock];
+      s1[q] = (q >= 2) ? v * rf : v;
+    }
+  }
+  const double dt2 = dt * dt, dt3 = dt2 * dt;
+  const bool o2 = P.tme_order >= 2, o3 = P.tme_order >= 3;
+  const double g1 = dt;                                                        // * tanh
+  const double g2 = 0.5 * dt + (o2 ? 0.5 * dt2 : 0.0);
+  const double g3 = (o2 ? 0.5 * dt2 : 0.0) + (o3 ? dt3 / 6.0 : 0.0);           // * tanh
+  const double g4 = (o2 ? 0.125 * dt2 : 0.0) + (o3 ? 0.25 * dt3 : 0.0);
+  const double g5 = o3 ? 0.125 * dt3 : 0.0;                                    // * tanh
+  const double g6 = o3 ? dt3 / 48.0 : 0.0;
+#pragma unroll
+  for (int p = 2 * N - 1; p >= 0; --p) {
+    double acc = s0[p];
+    if (p >= 1) acc = fma(g1, s1[p - 1], acc);
+    if (p >= 2) acc = fma(g2, s0[p - 2], acc);
+    if (p >= 3) acc = fma(g3, s1[p - 3], acc);
+    if (p >= 4) acc = fma(g4, s0[p - 4], acc);
+    if (p >= 5) acc = fma(g5, s1[p - 5], acc);
+    if (p >= 6) acc = fma(g6, s0[p - 6], acc);
+    ms[p] = acc;
+  }
+  times_factorials<N>(ms);
+}
+
 // The eigen-solve keeps (d, e, z) in registers.  -DMFS_Z_SMEM moves its first-row vector z to the (then dead) weight
 // rows of the shared-memory tile (16 registers fewer at N = 8); measured slower on B200 at every occupancy
 // (profiles/r2_ab_1d_kernel.md: N = 8, T = 100: 2.86e9 vs 3.01e9 filter-steps/s), kept as a build option.
@@ -337,7 +442,10 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   double mean, scale;
   double nell = 0.0;
   int status = -1;
-  bool have_atoms = false;
+  // what the next prediction starts from: 0 = the moments (a full quadrature), 1 = the posterior atoms in rows [0, 2N),
+  // 2 = the posterior moments + the tanh-weighted power sums in rows [2N, 4N) (fuses_update_and_predict)
+  constexpr bool kFuse = fuses_update_and_predict<MODE, KIND>();
+  int pred_from = 0;
   if (!park_in) {
     const double* ms0 = P.ms0 + row * P.ms0_stride;
 #pragma unroll
@@ -347,13 +455,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   } else {
 #pragma unroll
     for (int p = 0; p < 2 * N; ++p) ms[p] = park_in[p];
-#pragma unroll
-    for (int i = 0; i < 2 * N; ++i) sm[i * kBlock] = park_in[2 * N + i];   // atoms: w rows, then x rows
     mean = (MODE != MFS_MODE_RAW) ? park_in[4 * N] : 0.0;
     scale = (MODE == MFS_MODE_SCALED) ? park_in[4 * N + 1] : 1.0;
     nell = park_in[4 * N + 2];
     const double flag = park_in[4 * N + 3];
-    have_atoms = flag > 0.0;
+    pred_from = flag == 1.0 ? 1 : (flag == 2.0 && kFuse) ? 2 : 0;
+    const int row0 = pred_from == 2 ? 2 * N : 0;       // atoms (w rows, then x rows) or the power sums s1
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) sm[(row0 + i) * kBlock] = park_in[2 * N + i];
     if (flag < 0.0) status = (int)(-flag) - 1;   // failed in an earlier chunk: NaN from the first step of this one
   }
   const double* tprm = P.trans_params + row * P.trans_param_stride;
@@ -381,7 +490,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
       // posterior moments are tested (the same quantity the reference's Cholesky fails on -> NaN).  The literal
       // recursion (first step, MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE, stable=True) derives the rule from the moments.
       bool ok;
-      if (have_atoms) {
+      if (pred_from != 0) {
         double dj[N], ej[N];
         ok = jacobi_from_moments<N, false>(ms, dj, ej);          // pivot test only: ej is dead code here
       } else {
@@ -391,17 +500,33 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
         for (int i = 0; i < N; ++i) { sm[i * kBlock] = w[i]; sm[(N + i) * kBlock] = x[i]; }
       }
       if (ok) {
-        predict<N, MODE, KIND>(P, tp, sm, ms, mean, scale);
+        bool predicted = false;
+        if constexpr (kFuse) {
+          if (pred_from == 2) { predict_fused_raw_benes<N>(P, sm, ms); predicted = true; }
+        }
+        if (!predicted) predict<N, MODE, KIND>(P, tp, sm, ms, mean, scale);
         // Half-step 2, update (filtering.py:82-86)
         double w[N], x[N];
         ok = MFS_QUADRATURE(ms, mean, scale, w, x, P.stable != 0);
         if (ok) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) sm[(N + i) * kBlock] = x[i];
-          const double cc = update<N, MODE, MEAS>(P, mp, y, w, x, sm, ms, mean, scale);
-          nell -= log(cc);
           // stable=True always re-derives the prediction quadrature (its LDL completion is defined on the moments)
-          have_atoms = !(P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE) && !P.stable;
+          const bool literal = (P.flags & MFS_FLAG_RECOMPUTE_PREDICT_QUADRATURE) || P.stable;
+          double cc = 0.0;
+          bool updated = false;
+          if constexpr (kFuse) {
+            if (!literal) {
+              cc = update_fused_raw_benes<N, MEAS>(P, mp, y, w, x, sm, ms);
+              pred_from = 2;
+              updated = true;
+            }
+          }
+          if (!updated) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) sm[(N + i) * kBlock] = x[i];
+            cc = update<N, MODE, MEAS>(P, mp, y, w, x, sm, ms, mean, scale);
+            pred_from = literal ? 0 : 1;
+          }
+          nell -= log(cc);
         }
       }
       if (!ok) { status = (int)(P.t_offset + t); break; }
@@ -449,12 +574,13 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
     // alive at the end of a segment (or of a chunk: carry_out): park the state
 #pragma unroll
     for (int p = 0; p < 2 * N; ++p) park_out[p] = ms[p];
+    const int row0 = pred_from == 2 ? 2 * N : 0;
 #pragma unroll
-    for (int i = 0; i < 2 * N; ++i) park_out[2 * N + i] = sm[i * kBlock];
+    for (int i = 0; i < 2 * N; ++i) park_out[2 * N + i] = sm[(row0 + i) * kBlock];
     park_out[4 * N] = mean;
     park_out[4 * N + 1] = scale;
     park_out[4 * N + 2] = nell;
-    park_out[4 * N + 3] = have_atoms ? 1.0 : 0.0;
+    park_out[4 * N + 3] = (double)pred_from;
   }
   if (status < 0 && !G.last) {
     // alive at the end of a segment: enlist for the next one

@@ -12,7 +12,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_bounds', 'shard', 'gather_filters', 'argmin_over_shards', 'world', 'max_over_ranks']
+__all__ = ['shard_bounds', 'shard', 'gather_filters', 'argmin_over_shards', 'local_argmin', 'running_argmin', 'world',
+           'max_over_ranks']
 
 
 def world() -> Tuple[int, int]:
@@ -84,6 +85,18 @@ def local_argmin(nell: torch.Tensor, theta_offset: int = 0) -> Tuple[torch.Tenso
     clean = torch.where(torch.isnan(nell), torch.full_like(nell, float('inf')), nell)
     val, idx = clean.min(dim=0)
     return val, idx.to(torch.int64) + int(theta_offset)
+
+
+def running_argmin(best: Optional[Tuple[torch.Tensor, torch.Tensor]], nell: torch.Tensor, theta_offset: int = 0):
+    """Fold one chunk of a theta grid, a ``(n_theta_chunk, n_traj)`` nell table whose first row is global theta index
+    ``theta_offset``, into the running per-trajectory ``(min, argmin)``; ``best=None`` starts.  Chunks must arrive in
+    ascending theta order for ties to go to the smallest index (strict ``<``).  This is how a rank walks its slice of a
+    grid that does not fit one launch (BASELINE configs[3]: 512 x 512 theta x 10^3 records)."""
+    v, a = local_argmin(nell, theta_offset)
+    if best is None:
+        return v, a
+    upd = v < best[0]
+    return torch.where(upd, v, best[0]), torch.where(upd, a, best[1])
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -147,7 +147,9 @@ def test_per_record_grids_like_the_reference_experiment():
     rng = np.random.default_rng(5)
     B, T, n = 5, 8, 300
     dt = 1e-2
-    _, _, ic, logistic, pmf_o = O.benes_bernoulli(5)
+    _, _, _, logistic, pmf_o = O.benes_bernoulli(5)
+    from mfs_b200.one_dim.ss_models import benes_bernoulli
+    ic = benes_bernoulli(5)[3]
     ys = (rng.random((B, T)) < 0.5).astype(np.uint8)
     lb, ub = -3. - rng.random(B), 3. + rng.random(B)
     xs = np.stack([np.linspace(lb[k], ub[k], n) for k in range(B)])

@@ -98,3 +98,40 @@ def test_characteristic_fn_against_reference_golden():
     bad = g['mix5/raw/ms'].copy()
     bad[2] = bad[1] ** 2 - 1e-3
     assert np.isnan(characteristic_fn(zs, bad)).all()
+
+
+def test_kernel_elementary_functions_against_libm():
+    """exp / log / tanh as the kernels evaluate them (branch-free, polynomial coefficients in the constant bank) against
+    NumPy's libm: a couple of ulp, over the ranges the filters use and through the special cases."""
+    import ctypes
+    from mfs_b200 import _lib
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.uniform(-708., 708., 200000), rng.normal(size=200000) * 3., [0., -0., 1e-300, 707.9, -707.9,
+                        709.9, -745., 800., -800., np.inf, -np.inf, np.nan]])
+    xp = np.concatenate([np.exp(rng.uniform(-700., 700., 200000)), 1. + rng.uniform(0., 1e-3, 1000), rng.uniform(0.5, 2., 100000),
+                         [1., 2.2250738585072014e-308, 1e-310, 0., -1., np.inf, np.nan, 1.7976931348623157e308]])
+    L = _lib.lib()
+
+    def run(arr, which):
+        t = torch.from_numpy(arr).cuda()
+        o = torch.empty_like(t)
+        ptrs = [None, None, None]
+        ptrs[which] = ctypes.c_void_p(o.data_ptr())
+        _lib.check(L.mfs_math_selftest(t.numel(), ctypes.c_void_p(t.data_ptr()), *ptrs,
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return o.cpu().numpy()
+
+    with np.errstate(all='ignore'):
+        e, ref = run(x, 0), np.exp(x)
+        fin = np.isfinite(ref) & (ref > 1e-300)
+        assert np.max(np.abs(e[fin] - ref[fin]) / ref[fin]) < 4e-16
+        assert np.array_equal(np.isnan(e), np.isnan(ref)) and np.array_equal(np.isinf(e), np.isinf(ref))
+        assert np.all(e[~fin & ~np.isnan(ref) & ~np.isinf(ref)] < 1e-299)
+        lg, ref = run(xp, 1), np.log(xp)
+        fin = np.isfinite(ref)
+        assert np.max(np.abs(lg[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-3)) < 1e-15
+        assert np.max(np.abs(lg[fin] - ref[fin])) < 2e-13                      # |log| <= 745
+        assert np.array_equal(np.isnan(lg), np.isnan(ref)) and np.array_equal(lg[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
+        th, ref = run(x, 2), np.tanh(x)
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(th[ok] - ref[ok])) < 5e-16

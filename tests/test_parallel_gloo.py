@@ -52,6 +52,12 @@ def _worker(rank, world, port, total, n_theta, n_traj):
         assert torch.equal(gmin, clean.min(dim=0).values)
         assert torch.equal(garg, clean.argmin(dim=0))
         assert garg[2].item() == 5
+        # the same grid walked in chunks that do not fit one launch (bench.py secondary.theta_grid), then combined
+        best = None
+        for c0 in range(tlo, thi, 3):
+            best = parallel.running_argmin(best, nell[c0:min(thi, c0 + 3)], c0)
+        cmin, carg = parallel.argmin_over_shards(*best)
+        assert torch.equal(cmin, gmin) and torch.equal(carg, garg)
         assert abs(parallel.max_over_ranks(float(rank)) - (world - 1)) < 1e-12
     finally:
         dist.destroy_process_group()

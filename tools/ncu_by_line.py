@@ -1,6 +1,6 @@
 """Join the SASS page of an ncu report (per-instruction execution counts, stall samples, local-memory sectors) with the
 line table of the matching cubin (nvdisasm -g), by instruction index, and print dynamic totals per source line.
-usage: python tools/ncu_by_line.py report.ncu-rep kernel.cubin [top]"""
+usage: python tools/ncu_by_line.py report.ncu-rep kernel.cubin [top] [kernel-name-substring]"""
 import collections
 import csv
 import io
@@ -10,14 +10,24 @@ import sys
 
 rep, cubin = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+want = sys.argv[4] if len(sys.argv) > 4 else ''
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = next(r for r in rows if r and r[0] == 'Address')
 body = [r for r in rows if r and r[0].startswith('0x')]
 col = {n: i for i, n in enumerate(hdr)}
 dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout
-lines, cur = [], None
+lines, cur, inside = [], None, True
 for line in dis.splitlines():
+    m = re.match(r'\s*\.section\s+\.text\.(\S+?),', line)
+    if m:
+        inside = want in m.group(1)
+        continue
+    if re.match(r'\s*\.section\s', line):
+        inside = False
+        continue
+    if not inside:
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', line)
     if m:
         cur = (m.group(1).split('/')[-1], int(m.group(2)))

@@ -13,7 +13,7 @@ from mfs_b200.one_dim.ss_models import benes_bernoulli
 
 T = 100
 peak, _ = _lib.fp64_peak(0, 4096)
-print(f'# Round 1 — time profile over N (Benes-Bernoulli, TME-3, T = {T}, history = none, one B200; FP64 peak measured {peak / 1e12:.1f} TFLOP/s)\n')
+print(f'# Time profile over N (Benes-Bernoulli, TME-3, T = {T}, history = none, one B200; FP64 peak measured {peak / 1e12:.1f} TFLOP/s)\n')
 print('| N | filters | raw steps/s | central steps/s | diverged (raw) | W_reuse(N) flop/step | FP64 roofline frac (raw, all steps) |')
 print('|---|---|---|---|---|---|---|')
 for N in range(2, 16):
