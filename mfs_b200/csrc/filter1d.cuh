@@ -112,6 +112,17 @@ MFS_DEV void times_factorials(double (&ms)[2 * N]) {
 // Prediction: ms <- sum_i w_i T(x_i), with (mean, scale) <- predicted mean / scale in CENTRAL / SCALED modes.
 // The atoms are read from the shared-memory tile `sm` (w_i at row i, x_i at row N + i, scratch rows from 2N).
 // ---------------------------------------------------------------------------------------------------------------------
+// Loops over the N atoms that read the atoms from the shared-memory tile can stay ROLLED (the accumulators over the 2N
+// orders are the unrolled dimension): one copy of the per-atom code (an inlined exp is ~35 instructions) instead of N --
+// 1000 instructions (16 KB) less in the hot loop at N = 8.  Same operations in the same order, bit-identical results.
+// Same-box A/B (profiles/r2_ab_1d_rolled_atoms.log): N = 8 Benes +0.5 %, central +1.7 %, literal recursion +3.4 %,
+// N = 7 Normal family + Poisson +4.3 % (3.23e9 vs 3.09e9), N = 5 -4.8 % -> rolled from N = 7 on.
+#ifndef MFS_ROLL_ATOMS_FROM
+#define MFS_ROLL_ATOMS_FROM 7
+#endif
+template <int N>
+constexpr bool roll_atoms() { return N >= MFS_ROLL_ATOMS_FROM; }
+
 template <int N, int MODE, int KIND>
 MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, double* __restrict__ sm, double (&ms)[2 * N],
                      double& mean, double& scale) {
@@ -158,7 +169,7 @@ MFS_DEV void predict(const mfs_filter1d_args& P, const double* tprm, double* __r
     double s0[2 * N], s1[2 * N];
 #pragma unroll
     for (int q = 0; q < 2 * N; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
-#pragma unroll
+#pragma unroll (roll_atoms<N>() ? 1 : N)
     for (int i = 0; i < N; ++i) {
       const double wi = MFS_W(i), xi = MFS_X(i);
       const double tn = (MODE != MFS_MODE_RAW) ? MFS_A(i) : tanh_fast(xi);
@@ -288,6 +299,49 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
   if (MEAS == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) st.c0 = 0.0;
   else if (MEAS == MFS_MEAS_POISSON_SOFTPLUS) st.c0 = log_factorial(y);
   else st.c0 = (P.meas_id == MFS_MEAS_BERNOULLI_LOGISTIC_CUBIC) ? 0.0 : meas_step_constant(P.meas_id, y, mprm[1]);
+  if constexpr (roll_atoms<N>()) {
+  // atoms through the tile, rolled loops (same operations in the same order as the unrolled register version below)
+#pragma unroll
+  for (int i = 0; i < N; ++i) { sm[i * kBlock] = w[i]; sm[(N + i) * kBlock] = x[i]; }
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    const double u = sm[i * kBlock] * measurement_pdf_ct<MEAS>(P.meas_id, st, sm[(N + i) * kBlock], mprm);
+    sm[i * kBlock] = u;
+    cc += u;
+  }
+  const double cinv_r = 1.0 / cc;
+  double sinv_r = 1.0;
+  if (MODE != MFS_MODE_RAW) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) acc = fma(sm[i * kBlock], sm[(N + i) * kBlock], acc);
+    mean = acc * cinv_r;
+    if (MODE == MFS_MODE_SCALED) {
+      double v = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) { const double dlt = sm[(N + i) * kBlock] - mean; v = fma(sm[i * kBlock], dlt * dlt, v); }
+      scale = sqrt(v * cinv_r);
+      sinv_r = 1.0 / scale;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 2 * N; ++p) ms[p] = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    const double xi = sm[(N + i) * kBlock];
+    const double delta = (MODE == MFS_MODE_RAW) ? xi : (xi - mean) * sinv_r;
+    double pw = sm[i * kBlock];
+    sm[i * kBlock] = pw * cinv_r;
+#pragma unroll
+    for (int p = 0; p < 2 * N; ++p) {
+      ms[p] += pw;
+      pw *= delta;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 2 * N; ++p) ms[p] *= cinv_r;
+  return cc;
+  } else {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     w[i] = w[i] * measurement_pdf_ct<MEAS>(P.meas_id, st, x[i], mprm);   // u_i = w_i l_i
@@ -324,6 +378,7 @@ MFS_DEV double update(const mfs_filter1d_args& P, const double* mprm, double y, 
 #pragma unroll
   for (int p = 0; p < 2 * N; ++p) ms[p] *= cinv;
   return cc;
+  }
 }
 
 // Fused update (see fuses_update_and_predict): posterior raw moments AND the tanh-weighted power sums of the posterior

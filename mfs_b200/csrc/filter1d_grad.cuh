@@ -94,12 +94,14 @@ template <int P> MFS_DEV Dual<P> chain(const Dual<P>& a, double f, double df) {
   return r;
 }
 MFS_DEV double t_sqrt(double a) { return sqrt(a); }
-MFS_DEV double t_exp(double a) { return exp(a); }
-MFS_DEV double t_log(double a) { return log(a); }
+// exp / log: the branch-free constant-bank versions of models.cuh (<= 4e-16 / 1e-15 relative against libm, measured on the
+// device through mfs_math_selftest), libdevice outside their range
+MFS_DEV double t_exp(double a) { return exp_any(a); }
+MFS_DEV double t_log(double a) { return log_fast(a); }
 MFS_DEV double t_tanh(double a) { return tanh(a); }
 template <int P> MFS_DEV Dual<P> t_sqrt(const Dual<P>& a) { const double r = rsqrt_fast(a.v); return chain(a, a.v * r, 0.5 * r); }
-template <int P> MFS_DEV Dual<P> t_exp(const Dual<P>& a) { const double e = exp(a.v); return chain(a, e, e); }
-template <int P> MFS_DEV Dual<P> t_log(const Dual<P>& a) { return chain(a, log(a.v), rcp_fast(a.v)); }
+template <int P> MFS_DEV Dual<P> t_exp(const Dual<P>& a) { const double e = exp_any(a.v); return chain(a, e, e); }
+template <int P> MFS_DEV Dual<P> t_log(const Dual<P>& a) { return chain(a, log_fast(a.v), rcp_fast(a.v)); }
 template <int P> MFS_DEV Dual<P> t_tanh(const Dual<P>& a) { const double t = tanh(a.v); return chain(a, t, fma(-t, t, 1.0)); }
 
 template <class S> struct Scalar;
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
     // ---- update (filtering.py:81-86 / :150-158)
     ok = MFS_GRAD_QUADRATURE(ms, central ? mean : make_dual<P>(0.0), w, x);
     if (!ok) { status = (int32_t)t; break; }
-    const double lgam = (A.meas_id == MFS_MEAS_POISSON_SOFTPLUS) ? lgamma(y + 1.0) : 0.0;
+    const double lgam = (A.meas_id == MFS_MEAS_POISSON_SOFTPLUS) ? log_factorial(y) : 0.0;
     S cc = make_dual<P>(0.0);
     MFS_NODE_LOOP
     for (int i = 0; i < N; ++i) {

@@ -315,21 +315,53 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     // every sweep (measured: +8 % at N = 5, -4 % at N = 3, 4 -- profiles/r1_nd_occupancy.md).
     constexpr bool kRolled = S >= 15;
     double* Vr = V + k * SS + cc * S;
+    unsigned neg = 1u << (S - 1);            // bit i <=> coupling e[i] negligible; bit S-1 is a sentinel
+    double bound = 0.0;                      // Gershgorin bound of the spectrum: every |d| of the iteration stays below it
+    auto scan_couplings = [&]() {
+      neg = 1u << (S - 1);
+      bound = 0.0;
+#pragma unroll
+      for (int i = 0; i + 1 < S; ++i) {
+        if (fabs(qe[i]) <= kEps * (fabs(qd[i]) + fabs(qd[i + 1]))) neg |= 1u << i;
+        bound = fmax(bound, fabs(qd[i]) + fabs(qe[i]) + (i > 0 ? fabs(qe[i - 1]) : 0.0));
+      }
+      bound = fmax(bound, fabs(qd[S - 1]) + (S > 1 ? fabs(qe[S - 2]) : 0.0));
+    };
+    scan_couplings();
+    bool done = false, bad = false;
+#ifndef MFS_ND_NO_FAST_QL
+    // Round 2 fast path (S <= 16, i.e. N <= 5): when no coupling of the tridiagonal form is negligible at entry -- every
+    // step but the first few, where the initial product-like measure makes K_1 / K_2 degenerate -- the eigen-solve is the
+    // 1-D kernel's register chase (quadrature.cuh: ql_chase, compile-time indices, no split mask, no dynamic index, 26
+    // instructions per rotation instead of 76), run by every lane of the group on its own row z of V.  It never splits
+    // the interior: a chase through a small coupling is still an exact orthogonal similarity.  If it does not converge
+    // within its sweep budget (or meets an exactly decoupled block) the general loop below starts over from (qd, qe, z).
+    if constexpr (S <= 16) {
+      if (neg == (1u << (S - 1))) {
+        // on copies: a rotation whose f and g both vanish (an exactly decoupled block, which the general loop handles by
+        // splitting) would turn the state into NaN; the result is committed only if it converged with finite eigenvalues
+        double fd[S], fe[S], fz[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) { fd[i] = qd[i]; fe[i] = qe[i]; fz[i] = z[i]; }
+        bool ok = tridiag_ql_first_row<S, false>(fd, fe, fz);
+        double chk = 0.0;
+#pragma unroll
+        for (int i = 0; i < S; ++i) chk += fabs(fd[i]);          // identical in every lane of the group
+        ok = ok && (chk <= 1.79e308);
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < S; ++i) { qd[i] = fd[i]; z[i] = fz[i]; }
+          done = true;
+        }
+      }
+    }
+#endif
     if (kRolled && act) {
 #pragma unroll
       for (int c = 0; c < S; ++c) Vr[c] = z[c];
     }
-    unsigned neg = 1u << (S - 1);            // bit i <=> coupling e[i] negligible; bit S-1 is a sentinel
-    double bound = 0.0;                      // Gershgorin bound of the spectrum: every |d| of the iteration stays below it
-#pragma unroll
-    for (int i = 0; i + 1 < S; ++i) {
-      if (fabs(qe[i]) <= kEps * (fabs(qd[i]) + fabs(qd[i + 1]))) neg |= 1u << i;
-      bound = fmax(bound, fabs(qd[i]) + fabs(qe[i]) + (i > 0 ? fabs(qe[i - 1]) : 0.0));
-    }
-    bound = fmax(bound, fabs(qd[S - 1]) + (S > 1 ? fabs(qe[S - 2]) : 0.0));
     const double tiny = 2.0 * kEps * bound;
     int l = 0, iter = 0;
-    bool done = false, bad = false;
     for (;;) {
       int m = 0;
       if (!done) {
