@@ -18,7 +18,34 @@
 
 namespace mfs {
 
-constexpr int kNdWarps = 4;  // warps (filters) per CTA
+// warps (= filters) per CTA
+template <int N> constexpr int nd_warps() {
+#ifdef MFS_ND_WARPS
+  return N <= 5 ? MFS_ND_WARPS : 4;
+#else
+  return N == 5 ? 8 : 4;      // N = 5: 2 CTAs x 8 warps at 128 registers (profiles/r2_ab_nd_barrier.log)
+#endif
+}
+// deflation cascade of the register QL (quadrature.cuh): 0 = inlined per exit, 1 = shared guarded levels, 2 = shared switch
+#ifndef MFS_ND_CASCADE_SMALL
+#define MFS_ND_CASCADE_SMALL 0
+#endif
+#ifndef MFS_ND_CASCADE_LARGE
+#define MFS_ND_CASCADE_LARGE 0
+#endif
+// phase barriers per time step in filter_nd_kernel (0 = none; see the kernel).  Measured (profiles/r2_ab_nd_barrier.log):
+// N = 2: none is best (-1.5 % with any); N = 3: +6.5 % with 2, no more with 4; N = 4, 5: +15 / +22 % with 4;
+// N = 6, 7 (two / one CTA per SM): +-1 %.
+template <int N> constexpr int nd_step_barriers() {
+#ifdef MFS_ND_STEP_BARRIER
+  return MFS_ND_STEP_BARRIER;
+#else
+  return N <= 2 ? 0 : N == 3 ? 2 : N <= 5 ? 4 : 2;
+#endif
+}
+#ifndef MFS_ND_FAST_QL_MAX_S
+#define MFS_ND_FAST_QL_MAX_S 28   // largest S = N(N+1)/2 whose stage D tries the register QL first (28: every supported N)
+#endif
 
 struct NdArgs {
   int32_t mode;        // MFS_MODE_RAW / MFS_MODE_CENTRAL
@@ -142,8 +169,11 @@ struct NdDims {
 //   For S <= 16 the two matrices live in the two half-warps (stages B-D run once), otherwise they are processed one
 //   after the other with all 32 lanes.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int N>
-__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable) {   // one copy, two call sites
+// INNER: CTA barriers between the stages (after A, before each D), counted in nbar -- see the phase barriers of
+// filter_nd_kernel; a call that fails returns early and leaves the balance to the caller's catch-up loop.
+template <int N> constexpr int nd_inner_barriers() { return 1 + (NdDims<N>::S <= 16 ? 1 : 2); }
+template <int N, bool INNER = false>
+__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable, int64_t* nbar = nullptr) {   // one copy, two call sites
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
   constexpr unsigned kFull = 0xffffffffu;
@@ -207,6 +237,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     }
   }
   __syncwarp();
+  if constexpr (INNER) { __syncthreads(); ++*nbar; }
 
   constexpr int LPM = (S <= 16) ? 16 : 32;       // lanes per matrix
   constexpr int NPASS = (S <= 16) ? 1 : 2;
@@ -309,6 +340,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     }
     qd[S - 1] = __shfl_sync(kFull, a[S - 1], gbase + S - 1);
     qe[S - 1] = 0.0;
+    if constexpr (INNER) { __syncthreads(); ++*nbar; }
     // ---- D
     // Large S: the V rows go to shared memory and the chase below is a ROLLED loop (run-time index) of ~100
     // instructions that stays in the instruction cache, instead of S-1 unrolled bodies (22 KB at S = 15) re-fetched
@@ -329,37 +361,46 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     };
     scan_couplings();
     bool done = false, bad = false;
+    if (kRolled && act) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) Vr[c] = z[c];
+    }
 #ifndef MFS_ND_NO_FAST_QL
-    // Round 2 fast path (S <= 16, i.e. N <= 5): when no coupling of the tridiagonal form is negligible at entry -- every
-    // step but the first few, where the initial product-like measure makes K_1 / K_2 degenerate -- the eigen-solve is the
-    // 1-D kernel's register chase (quadrature.cuh: ql_chase, compile-time indices, no split mask, no dynamic index, 26
-    // instructions per rotation instead of 76), run by every lane of the group on its own row z of V.  It never splits
-    // the interior: a chase through a small coupling is still an exact orthogonal similarity.  If it does not converge
-    // within its sweep budget (or meets an exactly decoupled block) the general loop below starts over from (qd, qe, z).
-    if constexpr (S <= 16) {
+    // Round 2 fast path: when no coupling of the tridiagonal form is negligible at entry -- every step but the first
+    // few, where the initial product-like measure makes K_1 / K_2 degenerate -- the eigen-solve is the 1-D kernel's
+    // register chase (quadrature.cuh: ql_chase, compile-time indices, no split mask, no dynamic index, 26 instructions
+    // per rotation instead of 76), run by every lane of the group on its own row z of V.  It never splits the interior:
+    // a chase through a small coupling is still an exact orthogonal similarity.  If it does not converge within its
+    // sweep budget (or meets an exactly decoupled block) the general loop below starts over from (qd, qe, V).
+    if constexpr (S <= MFS_ND_FAST_QL_MAX_S) {
       if (neg == (1u << (S - 1))) {
         // on copies: a rotation whose f and g both vanish (an exactly decoupled block, which the general loop handles by
         // splitting) would turn the state into NaN; the result is committed only if it converged with finite eigenvalues
         double fd[S], fe[S], fz[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) { fd[i] = qd[i]; fe[i] = qe[i]; fz[i] = z[i]; }
-        bool ok = tridiag_ql_first_row<S, false>(fd, fe, fz);
+        bool ok = tridiag_ql_first_row<S, false, (S <= 16 ? MFS_ND_CASCADE_SMALL : MFS_ND_CASCADE_LARGE)>(fd, fe, fz);
         double chk = 0.0;
 #pragma unroll
         for (int i = 0; i < S; ++i) chk += fabs(fd[i]);          // identical in every lane of the group
         ok = ok && (chk <= 1.79e308);
         if (ok) {
 #pragma unroll
-          for (int i = 0; i < S; ++i) { qd[i] = fd[i]; z[i] = fz[i]; }
+          for (int i = 0; i < S; ++i) qd[i] = fd[i];
+          if constexpr (kRolled) {
+            if (act) {
+#pragma unroll
+              for (int c = 0; c < S; ++c) Vr[c] = fz[c];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < S; ++i) z[i] = fz[i];
+          }
           done = true;
         }
       }
     }
 #endif
-    if (kRolled && act) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) Vr[c] = z[c];
-    }
     const double tiny = 2.0 * kEps * bound;
     int l = 0, iter = 0;
     for (;;) {
@@ -587,11 +628,12 @@ MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scra
 #ifdef MFS_ND_MIN_BLOCKS
 template <int N> constexpr int nd_min_blocks() { return MFS_ND_MIN_BLOCKS; }
 #else
-template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N == 5 ? 3 : N == 6 ? 2 : 1; }
+template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N <= 6 ? 2 : 1; }
 #endif
 template <int N>
-__global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {
+__global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {
   using D = NdDims<N>;
+  constexpr int kNdWarps = nd_warps<N>();
   constexpr int S = D::S, SS = D::SS, Z = D::Z, M = D::M;
   extern __shared__ double smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -600,7 +642,28 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
   int* tab = reinterpret_cast<int*>(smem_all + kNdWarps * D::kDoubles);
   for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = __ldg(P.inds + e);
   __syncthreads();
-  if (b >= P.B) return;
+  // Phase barriers (nd_step_barriers<N>() per time step): the CTA's warps are independent filters, but left alone they
+  // drift apart (data-dependent sweep counts) and each streams the kernel's 250+ KB of unrolled code through the
+  // instruction caches on its own; re-aligning them a few times per step lets one fetch serve four warps
+  // (profiles/r2_ab_nd_barrier.log: +10..20 %).  Every warp executes exactly kBarriers * T barriers: a warp
+  // without a filter, or whose filter failed, runs the remaining ones in a catch-up loop before it leaves.
+  int64_t nbar = 0;
+  constexpr int kBarriers = nd_step_barriers<N>();
+#ifdef MFS_ND_INNER_BARRIER
+  constexpr bool kInner = kBarriers > 0;
+#else
+  constexpr bool kInner = false;
+#endif
+  const int64_t nbar_total = (int64_t)(kBarriers + (kInner ? 2 * nd_inner_barriers<N>() : 0)) * P.T;
+#define MFS_ND_PHASE_BARRIER(level)              \
+  if constexpr (kBarriers >= (level)) {          \
+    __syncthreads();                             \
+    ++nbar;                                      \
+  }
+  if (b >= P.B) {
+    for (; nbar < nbar_total; ++nbar) __syncthreads();
+    return;
+  }
   double* sm = smem_all + warp * D::kDoubles;
   double* ms = sm;
   double* scratch = sm + Z + SS;      // T and V of the quadrature (4 S^2 doubles), idle between quadratures
@@ -627,10 +690,12 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
   int status = -1, reason = 0;
   int64_t t = 0;
   for (; t < P.T; ++t) {
+    MFS_ND_PHASE_BARRIER(1)
     const double y = (double)__ldg(P.ys + b * P.T + t);
     // ---------------- prediction ----------------
-    int why = quadrature_nd<N>(sm, tab, lane, P.stable);
+    int why = quadrature_nd<N, kInner>(sm, tab, lane, P.stable, &nbar);
     if (why) { status = (int)t; reason = why; break; }
+    MFS_ND_PHASE_BARRIER(3)
     double acc[Z];
     const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
     const bool central = P.mode == MFS_MODE_CENTRAL;
@@ -666,8 +731,10 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
     __syncwarp();
     warp_reduce_moments<N>(acc, scratch, ms, 1.0, lane);
     // ---------------- update ----------------
-    why = quadrature_nd<N>(sm, tab, lane, P.stable);
+    MFS_ND_PHASE_BARRIER(2)
+    why = quadrature_nd<N, kInner>(sm, tab, lane, P.stable, &nbar);
     if (why) { status = (int)t; reason = why + 4; break; }
+    MFS_ND_PHASE_BARRIER(4)
     MeasStep st;
     st.y = y;
     st.c0 = 0.0;
@@ -718,6 +785,8 @@ __global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) filter_nd_k
       }
     }
   }
+  for (; nbar < nbar_total; ++nbar) __syncthreads();     // a failed filter: the barriers of the steps it did not run
+#undef MFS_ND_PHASE_BARRIER
   if (status >= 0) {
     const double qnan = nan("");
     nell = qnan; mean1 = qnan; mean2 = qnan;
@@ -764,8 +833,9 @@ struct NdQuadArgs {
 };
 
 template <int N>
-__global__ void __launch_bounds__(kNdWarps * 32, nd_min_blocks<N>()) quadrature_nd_kernel(const NdQuadArgs P) {
+__global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) quadrature_nd_kernel(const NdQuadArgs P) {
   using D = NdDims<N>;
+  constexpr int kNdWarps = nd_warps<N>();
   constexpr int S = D::S, SS = D::SS, Z = D::Z;
   extern __shared__ double smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

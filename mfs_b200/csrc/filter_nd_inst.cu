@@ -19,6 +19,7 @@ static cudaError_t opt_in_smem(Kernel kernel, bool (&configured)[64], size_t sme
 template <int N>
 cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream) {
   using D = NdDims<N>;
+  constexpr int kNdWarps = nd_warps<N>();
   const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
   static bool configured[64] = {};
   if (cudaError_t e = opt_in_smem(filter_nd_kernel<N>, configured, smem)) return e;
@@ -30,6 +31,7 @@ cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream) {
 template <int N>
 cudaError_t launch_quadrature_nd(const NdQuadArgs& a, cudaStream_t stream) {
   using D = NdDims<N>;
+  constexpr int kNdWarps = nd_warps<N>();
   const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
   static bool configured[64] = {};
   if (cudaError_t e = opt_in_smem(quadrature_nd_kernel<N>, configured, smem)) return e;

@@ -221,3 +221,32 @@ def test_paper_setting_N7_against_oracle():
     d = x - gs.mean
     lowest = [(w * d[:, 0] ** a * d[:, 1] ** b).sum() for a, b in mis[:6]]
     np.testing.assert_allclose(lowest, gs.cms[:6], atol=1e-9)
+
+
+@pytest.mark.parametrize('N', [3, 5, 6])
+def test_failed_and_missing_filters_do_not_disturb_their_cta(N):
+    """The 2-D kernel re-aligns the four warps (= four filters) of a CTA with barriers a few times per step.  A warp
+    whose filter fails (non-PD moments -> NaN from that step on) or that has no filter at all (ragged batch) must keep
+    those barriers balanced: the live filters next to it give bit-identical results to a run on their own, and nothing
+    hangs."""
+    mis = generate_graded_lexico_multi_indices(2, 2 * N - 1, 0)
+    inds = gram_and_hankel_indices_graded_lexico(N, 2)
+    dt, _, ts, gs, drift, dispersion, emission, pmf, simulate = prey_predator(mis)
+    fam = sde_cond_moments_tme_normal(drift, dispersion, dt, 2, mis)
+    B, T = 7, 9                                                     # 7 filters = one full CTA + one with a missing warp
+    rng = np.random.Generator(np.random.PCG64(31))
+    _, xs, ys = simulate(rng, integration_steps=10, T=T, n=B)
+    cms0 = np.tile(gs.cms, (B, 1))
+    bad = [1, 4, 6]
+    cms0[bad, 3] = -1e-3                                            # negative variance of x1: fails at step 0
+    out = moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, torch.from_numpy(ys).cuda(), (mis, inds), cms0,
+                               np.tile(gs.mean, (B, 1)), return_status=True)
+    cmss, means, nell, status = [o.cpu().numpy() if isinstance(o, torch.Tensor) else np.asarray(o) for o in out]
+    good = [k for k in range(B) if k not in bad]
+    assert np.all(status[bad] == 0) and np.all(np.isnan(nell[bad])) and np.all(np.isnan(cmss[bad]))
+    assert np.all(status[good] == -1) and np.all(np.isfinite(nell[good]))
+    for k in good:                                                  # each live filter alone (its CTA has 3 missing warps)
+        o = moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, torch.from_numpy(ys[k]).cuda(), (mis, inds), gs.cms,
+                                 gs.mean)
+        c1, m1, n1 = [x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in o]
+        assert np.array_equal(c1, cmss[k]) and np.array_equal(m1, means[k]) and n1 == nell[k]
