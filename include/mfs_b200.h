@@ -71,7 +71,8 @@ enum {
                          reference's consumers read from the history (dardel/prey_predator/mf.py:84-88,
                          dardel/benes_bernoulli/post_processing_mf.py:41-66): 16 B per step instead of 16 N.
                          raw: (m1, m2 - m1^2); central: (mean, cm2); scaled: (mean, scale^2 scm2).
-                         mean_out / scale_out are not written. */
+                         mean_out / scale_out are not written.
+                         2-D filter: ms_out[b][t][0..5) = (E x1, E x2, Var x1, Cov(x1, x2), Var x2). */
 };
 
 /* flags.
@@ -177,8 +178,8 @@ typedef struct mfs_filternd_args {
   const int32_t* inds;                                      /* [3][s][s] */
   int32_t out_mode;      /* MFS_OUT_* */
   int32_t stable;        /* 0/1: `stable=True`, LDL completion of the Gram factor (mfs/utils.py:526-538) */
-  double* ms_out;        /* FULL [B][T][z] | LAST [B][z] */
-  double* mean_out;      /* FULL [B][T][2] | LAST [B][2] */
+  double* ms_out;        /* FULL [B][T][z] | LAST [B][z] | MEANVAR [B][T][5] */
+  double* mean_out;      /* FULL [B][T][2] | LAST [B][2] (CENTRAL; not written in MEANVAR / NONE) */
   double* nell_out;      /* [B] */
   int32_t* status_out;   /* [B] or NULL */
 } mfs_filternd_args;

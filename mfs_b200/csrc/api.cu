@@ -670,8 +670,10 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream) {
   if (a->B == 0) return 0;
   if (!a->trans_params || !a->meas_params || !a->ms0 || !a->inds || !a->nell_out || (a->T > 0 && !a->ys))
     return fail("NULL pointer argument");
-  if (a->mode == MFS_MODE_CENTRAL && (!a->mean0 || (a->out_mode != MFS_OUT_NONE && !a->mean_out))) return fail("mean0 / mean_out is NULL in central mode");
-  if (a->out_mode != MFS_OUT_NONE && !a->ms_out) return fail("ms_out is NULL");
+  if (a->out_mode < MFS_OUT_FULL || a->out_mode > MFS_OUT_MEANVAR) return fail("unknown out_mode %d", a->out_mode);
+  const bool nd_aux = a->out_mode == MFS_OUT_FULL || a->out_mode == MFS_OUT_LAST;    // MEANVAR carries the means in ms_out
+  if (a->mode == MFS_MODE_CENTRAL && (!a->mean0 || (nd_aux && !a->mean_out))) return fail("mean0 / mean_out is NULL in central mode");
+  if (a->out_mode != MFS_OUT_NONE && !a->ms_out && !(a->out_mode == MFS_OUT_MEANVAR && a->T == 0)) return fail("ms_out is NULL");
   NdArgs k;
   k.mode = a->mode; k.trans_id = a->trans_id; k.tme_order = a->tme_order; k.meas_id = a->meas_id; k.obs_dim = a->obs_dim;
   k.out_mode = a->out_mode; k.stable = a->stable ? 1 : 0; k.B = a->B; k.T = a->T; k.dt = a->dt;

@@ -169,11 +169,133 @@ struct NdDims {
 //   For S <= 16 the two matrices live in the two half-warps (stages B-D run once), otherwise they are processed one
 //   after the other with all 32 lanes.
 // ---------------------------------------------------------------------------------------------------------------------
-// INNER: CTA barriers between the stages (after A, before each D), counted in nbar -- see the phase barriers of
-// filter_nd_kernel; a call that fails returns early and leaves the balance to the caller's catch-up loop.
-template <int N> constexpr int nd_inner_barriers() { return 1 + (NdDims<N>::S <= 16 ? 1 : 2); }
-template <int N, bool INNER = false>
-__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable, int64_t* nbar = nullptr) {   // one copy, two call sites
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-batched stage D (MFS_ND_BATCHED_QL, S in [10, 16]): the scalar QL recurrence of a matrix is the same in all 16
+// lanes of its group, i.e. 17 of the 21 FP64 operations of a rotation are executed 16 times for nothing.  Here the
+// CTA's warps (phase-aligned anyway) hand their 2 x nd_warps matrices to warp 0, whose lanes run ONE recurrence each
+// (per-lane control flow as in the 1-D kernel: ql_run_recorded) and record the rotations of up to kSweeps sweeps; then
+// every warp applies the recorded sweeps to its rows of V (1 broadcast load + 4 FP64 per rotation) -- until all
+// matrices are done.  Buffers: the warp's own R and T regions, which are idle during stage D:
+//   R region: per matrix k = 0, 1: d[S], e[S], {l, iter, dl, dl1, el}; then ints {state[2], nsw[2]}
+//   T[k]:     double2 rec[kSweeps][S], then ints rec_l[kSweeps]
+// A warp with nothing to solve (failed / missing filter, Cholesky failure, a split matrix that needs the general loop)
+// takes part with take = false: the barriers of the protocol are executed by every warp of the CTA.
+template <int N>
+struct NdBatch {
+  using D = NdDims<N>;
+  static constexpr int S = D::S, SS = D::SS;
+  static constexpr int kMat = 2 * S + 5;
+  static constexpr int kSweeps = (SS - 4) / (2 * S) > 7 ? 7 : (SS - 4) / (2 * S);
+  static constexpr bool kEnabled = S >= 10 && S <= 16;
+  enum { SKIP = 0, RUN = 1, DONE = 2, FAILED = 3 };
+  static_assert(!kEnabled || 2 * kMat + 2 <= SS, "R region too small");
+  static_assert(!kEnabled || 2 * kSweeps * S + (kSweeps + 1) / 2 <= SS, "T region too small");
+};
+
+// LIVE = false: participant without matrices.  Returns (per half-warp) whether its matrix was solved; then fd holds the
+// eigenvalues and fz the lane's row of V Q.
+template <int N, bool LIVE>
+MFS_DEV bool nd_batched_ql(double* __restrict__ cta_base, const int warp, const int lane, const bool take,
+                           const double (&qd)[NdDims<N>::S], const double (&qe)[NdDims<N>::S],
+                           double (&fz)[NdDims<N>::S], double (&fd)[NdDims<N>::S]) {
+  using NB = NdBatch<N>;
+  using D = NdDims<N>;
+  constexpr int S = D::S, SS = D::SS, W = nd_warps<N>(), K = NB::kSweeps, kMat = NB::kMat;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(2 * W <= 32, "one lane per matrix");
+  const int k = lane >> 4, r = lane & 15;
+  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::Z; };
+  auto region_T = [&](int w, int kk) { return cta_base + w * D::kDoubles + D::Z + SS + kk * SS; };
+  auto flags_of = [&](int w) { return reinterpret_cast<int*>(region_R(w) + 2 * kMat); };
+  int* const all_done = reinterpret_cast<int*>(cta_base + D::Z + 5 * SS + SS + 2 * S);      // warp 0's hv[0]
+  int* const my_flags = flags_of(warp);
+  if (LIVE) {
+    if (r == 0) {
+      double* q = region_R(warp) + k * kMat;
+#pragma unroll
+      for (int i = 0; i < S; ++i) { q[i] = qd[i]; q[S + i] = qe[i]; }
+      q[2 * S] = -1.0;                                   // l < 0: not started
+      my_flags[k] = take ? NB::RUN : NB::SKIP;
+      my_flags[2 + k] = 0;
+    }
+  } else {
+    if (lane < 2) { my_flags[lane] = NB::SKIP; my_flags[2 + lane] = 0; }
+  }
+  __syncthreads();
+  for (;;) {
+    if (warp == 0) {
+      int running = 0;
+      if (lane < 2 * W) {
+        int* fl = flags_of(lane >> 1);
+        const int kk = lane & 1;
+        if (fl[kk] == NB::RUN) {
+          double* q = region_R(lane >> 1) + kk * kMat;
+          double d[S], e[S];
+#pragma unroll
+          for (int i = 0; i < S; ++i) { d[i] = q[i]; e[i] = q[S + i]; }
+          int l = (int)q[2 * S], iter = (int)q[2 * S + 1];
+          double dl = q[2 * S + 2], dl1 = q[2 * S + 3], el = q[2 * S + 4];
+          double2* rec = reinterpret_cast<double2*>(region_T(lane >> 1, kk));
+          int* rec_l = reinterpret_cast<int*>(region_T(lane >> 1, kk) + 2 * K * S);
+          int nsw = 0;
+          const int st = ql_run_recorded<S>(d, e, l, iter, dl, dl1, el, K, rec, rec_l, nsw);
+#pragma unroll
+          for (int i = 0; i < S; ++i) { q[i] = d[i]; q[S + i] = e[i]; }
+          q[2 * S] = (double)l; q[2 * S + 1] = (double)iter; q[2 * S + 2] = dl; q[2 * S + 3] = dl1; q[2 * S + 4] = el;
+          fl[2 + kk] = nsw;
+          fl[kk] = st == 0 ? NB::RUN : st == 1 ? NB::DONE : NB::FAILED;
+          running = st == 0;
+        } else {
+          fl[2 + kk] = 0;
+        }
+      }
+      const int any = __any_sync(kFull, running);
+      if (lane == 0) *all_done = !any;
+    }
+    __syncthreads();
+    if (LIVE) {
+      const int nsw = my_flags[2 + k];
+      const double2* rec = reinterpret_cast<const double2*>(region_T(warp, k));
+      const int* rec_l = reinterpret_cast<const int*>(region_T(warp, k) + 2 * K * S);
+      for (int sw = 0; sw < nsw; ++sw) {
+        const int l = rec_l[sw];
+#pragma unroll
+        for (int I = S - 2; I >= 0; --I) {
+          if (I >= l) {
+            const double2 cs = rec[sw * S + I];
+            const double zi1 = fz[I + 1];
+            fz[I + 1] = fma(cs.y, fz[I], cs.x * zi1);
+            fz[I] = fma(cs.x, fz[I], -cs.y * zi1);
+          }
+        }
+      }
+    }
+    const int done = *all_done;
+    __syncthreads();
+    if (done) break;
+  }
+  if (LIVE) {
+    if (my_flags[k] == NB::DONE) {
+      const double* q = region_R(warp) + k * kMat;
+#pragma unroll
+      for (int i = 0; i < S; ++i) fd[i] = q[i];
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int N>
+MFS_DEV void nd_batched_ql_idle(double* __restrict__ cta_base, const int warp, const int lane) {
+  double u0[NdDims<N>::S], u1[NdDims<N>::S], u2[NdDims<N>::S], u3[NdDims<N>::S];      // never touched (LIVE = false)
+  nd_batched_ql<N, false>(cta_base, warp, lane, false, u0, u1, u2, u3);
+}
+
+// BATCH: stage D through the CTA-batched protocol (nd_batched_ql): EVERY warp of the CTA must then make the same calls
+// (a warp without a live filter calls nd_batched_ql_idle instead); cta_base = start of the CTA's shared memory.
+template <int N, bool BATCH = false>
+__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable,
+                                          double* cta_base = nullptr, int warp = 0) {   // one copy, two call sites
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
   constexpr unsigned kFull = 0xffffffffu;
@@ -197,7 +319,10 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
 #pragma unroll
       for (int j = 0; j < S; ++j) {
         const double piv = __shfl_sync(kFull, g[j], j);
-        if (!(piv > 0.0)) return 1;
+        if (!(piv > 0.0)) {
+          if constexpr (BATCH) nd_batched_ql_idle<N>(cta_base, warp, lane);
+          return 1;
+        }
         const double rinv = rsqrt_fast(piv);
         rdi[j] = rinv;
         g[j] *= rinv;                                   // L[r][j] for r >= j
@@ -218,7 +343,10 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
 #pragma unroll
       for (int j = 0; j < S; ++j) {
         const double piv = __shfl_sync(kFull, g[j], j);                  // d_j
-        if (!(piv == piv)) return 1;
+        if (!(piv == piv)) {
+          if constexpr (BATCH) nd_batched_ql_idle<N>(cta_base, warp, lane);
+          return 1;
+        }
         const double sj = (piv < 0.0) ? eps : sqrt(piv);
         rdi[j] = 1.0 / sj;
         const double gj = g[j];                                          // l_rj d_j
@@ -237,7 +365,6 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     }
   }
   __syncwarp();
-  if constexpr (INNER) { __syncthreads(); ++*nbar; }
 
   constexpr int LPM = (S <= 16) ? 16 : 32;       // lanes per matrix
   constexpr int NPASS = (S <= 16) ? 1 : 2;
@@ -340,7 +467,6 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     }
     qd[S - 1] = __shfl_sync(kFull, a[S - 1], gbase + S - 1);
     qe[S - 1] = 0.0;
-    if constexpr (INNER) { __syncthreads(); ++*nbar; }
     // ---- D
     // Large S: the V rows go to shared memory and the chase below is a ROLLED loop (run-time index) of ~100
     // instructions that stays in the instruction cache, instead of S-1 unrolled bodies (22 KB at S = 15) re-fetched
@@ -372,7 +498,32 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     // per rotation instead of 76), run by every lane of the group on its own row z of V.  It never splits the interior:
     // a chase through a small coupling is still an exact orthogonal similarity.  If it does not converge within its
     // sweep budget (or meets an exactly decoupled block) the general loop below starts over from (qd, qe, V).
-    if constexpr (S <= MFS_ND_FAST_QL_MAX_S) {
+    if constexpr (BATCH) {
+      // every warp of the CTA is here (or in nd_batched_ql_idle) at the same time
+      const bool take = neg == (1u << (S - 1));
+      double fd[S], fz[S];
+#pragma unroll
+      for (int i = 0; i < S; ++i) fz[i] = z[i];
+      bool ok = nd_batched_ql<N, true>(cta_base, warp, lane, take, qd, qe, fz, fd);
+      double chk = 0.0;
+#pragma unroll
+      for (int i = 0; i < S; ++i) chk += fabs(ok ? fd[i] : 0.0);
+      ok = ok && (chk <= 1.79e308);
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) qd[i] = fd[i];
+        if constexpr (kRolled) {
+          if (act) {
+#pragma unroll
+            for (int c = 0; c < S; ++c) Vr[c] = fz[c];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < S; ++i) z[i] = fz[i];
+        }
+        done = true;
+      }
+    } else if constexpr (S <= MFS_ND_FAST_QL_MAX_S) {
       if (neg == (1u << (S - 1))) {
         // on copies: a rotation whose f and g both vanish (an exactly decoupled block, which the general loop handles by
         // splitting) would turn the state into NaN; the result is committed only if it converged with finite eigenvalues
@@ -644,24 +795,35 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
   __syncthreads();
   // Phase barriers (nd_step_barriers<N>() per time step): the CTA's warps are independent filters, but left alone they
   // drift apart (data-dependent sweep counts) and each streams the kernel's 250+ KB of unrolled code through the
-  // instruction caches on its own; re-aligning them a few times per step lets one fetch serve four warps
-  // (profiles/r2_ab_nd_barrier.log: +10..20 %).  Every warp executes exactly kBarriers * T barriers: a warp
-  // without a filter, or whose filter failed, runs the remaining ones in a catch-up loop before it leaves.
-  int64_t nbar = 0;
+  // instruction caches on its own; re-aligning them a few times per step lets one fetch serve all warps of the CTA
+  // (profiles/r2_ab_nd_barrier.log: +10..20 %).  A step is the fixed sequence  B1 Q B3 B2 Q B4  (B = barrier if enabled,
+  // Q = a quadrature, which in the CTA-batched build contains barriers of its own); a warp without a filter, or whose
+  // filter failed, runs the rest of that sequence as a participant without work (zombie_rest) before it leaves.
   constexpr int kBarriers = nd_step_barriers<N>();
-#ifdef MFS_ND_INNER_BARRIER
-  constexpr bool kInner = kBarriers > 0;
+#ifdef MFS_ND_BATCHED_QL
+  constexpr bool kBatch = NdBatch<N>::kEnabled;
 #else
-  constexpr bool kInner = false;
+  constexpr bool kBatch = false;
 #endif
-  const int64_t nbar_total = (int64_t)(kBarriers + (kInner ? 2 * nd_inner_barriers<N>() : 0)) * P.T;
-#define MFS_ND_PHASE_BARRIER(level)              \
-  if constexpr (kBarriers >= (level)) {          \
-    __syncthreads();                             \
-    ++nbar;                                      \
-  }
+#define MFS_ND_PHASE_BARRIER(level) \
+  if constexpr (kBarriers >= (level)) __syncthreads();
+  auto zombie_rest = [&](const int64_t t0, int stage) {   // 0: whole steps from t0; 1 / 2: step t0 after its first / second quadrature
+    for (int64_t tt = t0; tt < P.T; ++tt) {
+      if (stage == 0) {
+        MFS_ND_PHASE_BARRIER(1)
+        if constexpr (kBatch) nd_batched_ql_idle<N>(smem_all, warp, lane);
+      }
+      if (stage <= 1) {
+        MFS_ND_PHASE_BARRIER(3)
+        MFS_ND_PHASE_BARRIER(2)
+        if constexpr (kBatch) nd_batched_ql_idle<N>(smem_all, warp, lane);
+      }
+      MFS_ND_PHASE_BARRIER(4)
+      stage = 0;
+    }
+  };
   if (b >= P.B) {
-    for (; nbar < nbar_total; ++nbar) __syncthreads();
+    zombie_rest(0, 0);
     return;
   }
   double* sm = smem_all + warp * D::kDoubles;
@@ -687,14 +849,14 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
   // The graded-lex position of (a, b) is (a+b)(a+b+1)/2 + a for d = 2; the host verifies that the tables it was given
   // (multi_indices, inds) are in that order, so the accumulators below can use compile-time positions.
   double nell = 0.0;
-  int status = -1, reason = 0;
+  int status = -1, reason = 0, fail_stage = 0;
   int64_t t = 0;
   for (; t < P.T; ++t) {
     MFS_ND_PHASE_BARRIER(1)
     const double y = (double)__ldg(P.ys + b * P.T + t);
     // ---------------- prediction ----------------
-    int why = quadrature_nd<N, kInner>(sm, tab, lane, P.stable, &nbar);
-    if (why) { status = (int)t; reason = why; break; }
+    int why = quadrature_nd<N, kBatch>(sm, tab, lane, P.stable, smem_all, warp);
+    if (why) { status = (int)t; reason = why; fail_stage = 1; break; }
     MFS_ND_PHASE_BARRIER(3)
     double acc[Z];
     const bool tme_full = P.trans_id == MFS_TRANS_TME;   // TME without the Normal approximation
@@ -732,8 +894,8 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
     warp_reduce_moments<N>(acc, scratch, ms, 1.0, lane);
     // ---------------- update ----------------
     MFS_ND_PHASE_BARRIER(2)
-    why = quadrature_nd<N, kInner>(sm, tab, lane, P.stable, &nbar);
-    if (why) { status = (int)t; reason = why + 4; break; }
+    why = quadrature_nd<N, kBatch>(sm, tab, lane, P.stable, smem_all, warp);
+    if (why) { status = (int)t; reason = why + 4; fail_stage = 2; break; }
     MFS_ND_PHASE_BARRIER(4)
     MeasStep st;
     st.y = y;
@@ -783,9 +945,20 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
         P.mean_out[(b * P.T + t) * 2] = mean1;
         P.mean_out[(b * P.T + t) * 2 + 1] = mean2;
       }
+    } else if (P.out_mode == MFS_OUT_MEANVAR) {
+      // (E x1, E x2, Var x1, Cov(x1, x2), Var x2): graded-lex positions (0,1) = 1, (1,0) = 2, (0,2) = 3, (1,1) = 4, (2,0) = 5
+      if (lane == 0) {
+        double* o = P.ms_out + (b * P.T + t) * 5;
+        if (P.mode == MFS_MODE_CENTRAL) {
+          o[0] = mean1; o[1] = mean2; o[2] = ms[5]; o[3] = ms[4]; o[4] = ms[3];
+        } else {
+          const double e1 = ms[2], e2 = ms[1];
+          o[0] = e1; o[1] = e2; o[2] = fma(-e1, e1, ms[5]); o[3] = fma(-e1, e2, ms[4]); o[4] = fma(-e2, e2, ms[3]);
+        }
+      }
     }
   }
-  for (; nbar < nbar_total; ++nbar) __syncthreads();     // a failed filter: the barriers of the steps it did not run
+  if (status >= 0) zombie_rest(t, fail_stage);     // a failed filter: the rest of the CTA's barrier sequence
 #undef MFS_ND_PHASE_BARRIER
   if (status >= 0) {
     const double qnan = nan("");
@@ -793,6 +966,9 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
     __syncwarp();
     for (int e = lane; e < Z; e += 32) ms[e] = qnan;
     __syncwarp();
+    if (P.out_mode == MFS_OUT_MEANVAR) {
+      for (int64_t e = t * 5 + lane; e < P.T * 5; e += 32) P.ms_out[b * P.T * 5 + e] = qnan;
+    }
     if (P.out_mode == MFS_OUT_FULL) {
       for (; t < P.T; ++t) {
         double* o = P.ms_out + (b * P.T + t) * Z;

@@ -98,11 +98,12 @@ def _run(mode, spec, meas, ys, moments_partial_order, ms0, mean0, stable, histor
     nell = torch.empty(B, **f64)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     ms_out = mean_out = None
-    tail = (T,) if history == 'full' else ()
+    tail = (T,) if history in ('full', 'meanvar') else ()
+    width = 5 if history == 'meanvar' else z
     if history != 'none':
-        ms_out = torch.empty((B,) + tail + (z,), **f64)
+        ms_out = torch.empty((B,) + tail + (width,), **f64)
         a.ms_out = ms_out.data_ptr()
-        if mode == 'central':
+        if mode == 'central' and history != 'meanvar':
             mean_out = torch.empty((B,) + tail + (2,), **f64)
             a.mean_out = mean_out.data_ptr()
     a.nell_out, a.status_out = nell.data_ptr(), status.data_ptr()
@@ -118,12 +119,14 @@ def _run(mode, spec, meas, ys, moments_partial_order, ms0, mean0, stable, histor
         t = t.reshape(batch_shape + tl)
         return t.cpu().numpy() if is_np else t
 
-    return fin(ms_out, tail + (z,)), fin(mean_out, tail + (2,)), fin(nell, ()), fin(status, ())
+    return fin(ms_out, tail + (width,)), fin(mean_out, tail + (2,)), fin(nell, ()), fin(status, ())
 
 
 def moment_filter_nd_rms(state_cond_raw_moments, measurement_cond_pdf, ys, moments_partial_order, rms0,
                          stable: bool = False, *, history: str = 'full', return_status: bool = False):
-    """Mirror of ``mfs/multi_dims/filtering.py:283-344``.  Returns ``(rmss (..., T, z), nell (...))``."""
+    """Mirror of ``mfs/multi_dims/filtering.py:283-344``.  Returns ``(rmss (..., T, z), nell (...))``.
+    ``history='meanvar'``: ``rmss`` is ``(..., T, 5)`` = (E x1, E x2, Var x1, Cov, Var x2) per step -- what the reference's
+    consumer keeps (``dardel/prey_predator/mf.py:84-88``); ``'last'`` / ``'none'``: final moments only / nell only."""
     spec = _check(state_cond_raw_moments, 'raw')
     ms, _, nell, status = _run('raw', spec, measurement_cond_pdf, ys, moments_partial_order, rms0, None, stable,
                                history, return_status)
@@ -132,7 +135,8 @@ def moment_filter_nd_rms(state_cond_raw_moments, measurement_cond_pdf, ys, momen
 
 def moment_filter_nd_cms(state_cond_central_moments, state_cond_mean, measurement_cond_pdf, ys, moments_partial_order,
                          cms0, mean0, stable: bool = False, *, history: str = 'full', return_status: bool = False):
-    """Mirror of ``mfs/multi_dims/filtering.py:210-280``.  Returns ``(cmss (..., T, z), means (..., T, d), nell)``."""
+    """Mirror of ``mfs/multi_dims/filtering.py:210-280``.  Returns ``(cmss (..., T, z), means (..., T, d), nell)``.
+    ``history='meanvar'``: ``cmss`` is ``(..., T, 5)`` = (E x1, E x2, Var x1, Cov, Var x2) per step and ``means`` is None."""
     spec = _check(state_cond_central_moments, 'central')
     if not isinstance(state_cond_mean, TransitionFunctorND) or state_cond_mean.role != 'mean' \
             or state_cond_mean.spec is not spec:

@@ -250,3 +250,43 @@ def test_failed_and_missing_filters_do_not_disturb_their_cta(N):
                                  gs.mean)
         c1, m1, n1 = [x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in o]
         assert np.array_equal(c1, cmss[k]) and np.array_equal(m1, means[k]) and n1 == nell[k]
+
+
+@pytest.mark.parametrize('mode', ['raw', 'central'])
+def test_meanvar_history(mode):
+    """history='meanvar' (MFS_OUT_MEANVAR for the 2-D filter): (E x1, E x2, Var x1, Cov, Var x2) per step, bit-identical
+    to what the full history gives; NaN from the failing step on."""
+    N, B, T = 4, 6, 11
+    mis = generate_graded_lexico_multi_indices(2, 2 * N - 1, 0)
+    inds = gram_and_hankel_indices_graded_lexico(N, 2)
+    dt, _, ts, gs, drift, dispersion, emission, pmf, simulate = prey_predator(mis)
+    fam = sde_cond_moments_tme_normal(drift, dispersion, dt, 2, mis)
+    rng = np.random.Generator(np.random.PCG64(5))
+    _, xs, ys = simulate(rng, integration_steps=10, T=T, n=B)
+    ys_t = torch.from_numpy(ys).cuda()
+    if mode == 'raw':
+        ms0 = np.tile(gs.rms, (B, 1))
+        ms0[2, 3] = ms0[2, 1] ** 2 - 1e-3                          # record 2 fails at step 0
+        full, nell = moment_filter_nd_rms((fam[0], 'index'), pmf, ys_t, (mis, inds), ms0)
+        mv, nell2, st = moment_filter_nd_rms((fam[0], 'index'), pmf, ys_t, (mis, inds), ms0, history='meanvar',
+                                             return_status=True)
+        full = full.cpu().numpy()
+        e1, e2 = full[..., 2], full[..., 1]
+        want = np.stack([e1, e2, full[..., 5] - e1 * e1, full[..., 4] - e1 * e2, full[..., 3] - e2 * e2], axis=-1)
+        tol = dict(rtol=1e-12, atol=1e-15)                         # fma vs separate multiply in the variance
+    else:
+        ms0 = np.tile(gs.cms, (B, 1))
+        ms0[2, 3] = -1e-3
+        full, means, nell = moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, ys_t, (mis, inds), ms0,
+                                                 np.tile(gs.mean, (B, 1)))
+        mv, none, nell2, st = moment_filter_nd_cms((fam[1], 'index'), fam[3], pmf, ys_t, (mis, inds), ms0,
+                                                   np.tile(gs.mean, (B, 1)), history='meanvar', return_status=True)
+        assert none is None
+        full, means = full.cpu().numpy(), means.cpu().numpy()
+        want = np.stack([means[..., 0], means[..., 1], full[..., 5], full[..., 4], full[..., 3]], axis=-1)
+        tol = dict(rtol=0, atol=0)
+    mv, st = mv.cpu().numpy(), st.cpu().numpy()
+    assert mv.shape == (B, T, 5) and st[2] == 0 and np.all(np.isnan(mv[2]))
+    ok = st < 0
+    np.testing.assert_allclose(mv[ok], want[ok], **tol)
+    assert np.array_equal(nell.cpu().numpy(), nell2.cpu().numpy(), equal_nan=True)
