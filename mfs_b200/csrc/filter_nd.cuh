@@ -33,6 +33,11 @@ template <int N> constexpr int nd_warps() {
 #ifndef MFS_ND_CASCADE_LARGE
 #define MFS_ND_CASCADE_LARGE 0
 #endif
+// re-associated rotation with the 7-deep dependency chain in the register QL (quadrature.cuh: ql_chase7) for S >= this.
+// Measured (profiles/r2_ab_nd_batched_chain7.log): N = 7 (4 warps per SM, latency bound) +3 %; N = 3..6: -2 .. -8 %.
+#ifndef MFS_ND_QL_CHAIN7_MIN_S
+#define MFS_ND_QL_CHAIN7_MIN_S 28
+#endif
 // phase barriers per time step in filter_nd_kernel (0 = none; see the kernel).  Measured (profiles/r2_ab_nd_barrier.log):
 // N = 2: none is best (-1.5 % with any); N = 3: +6.5 % with 2, no more with 4; N = 4, 5: +15 / +22 % with 4;
 // N = 6, 7 (two / one CTA per SM): +-1 %.
@@ -189,8 +194,52 @@ struct NdBatch {
   static constexpr bool kEnabled = S >= 10 && S <= 16;
   enum { SKIP = 0, RUN = 1, DONE = 2, FAILED = 3 };
   static_assert(!kEnabled || 2 * kMat + 2 <= SS, "R region too small");
-  static_assert(!kEnabled || 2 * kSweeps * S + (kSweeps + 1) / 2 <= SS, "T region too small");
+  static_assert(!kEnabled || 1 + 2 * kSweeps * S + (kSweeps + 1) / 2 <= SS, "T region too small");
 };
+
+// The scalar phase of nd_batched_ql (warp 0 only): lane m runs up to kSweeps recorded sweeps of matrix m = 2 w + k.  One
+// out-of-line copy: the protocol is instantiated at several call sites (live, idle, Cholesky failure).
+template <int N>
+__device__ __noinline__ void nd_batched_scalar_phase(double* __restrict__ cta_base, const int lane) {
+  using NB = NdBatch<N>;
+  using D = NdDims<N>;
+  constexpr int S = D::S, SS = D::SS, W = nd_warps<N>(), K = NB::kSweeps, kMat = NB::kMat;
+  constexpr unsigned kFull = 0xffffffffu;
+  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::Z; };
+  auto region_T = [&](int w, int kk) {       // 16-byte aligned (double2 records): Z + SS may be odd
+    double* t = cta_base + w * D::kDoubles + D::Z + SS + kk * SS;
+    return t + ((reinterpret_cast<uintptr_t>(t) >> 3) & 1);
+  };
+  auto flags_of = [&](int w) { return reinterpret_cast<int*>(region_R(w) + 2 * kMat); };
+  int* const all_done = reinterpret_cast<int*>(cta_base + D::Z + 5 * SS + SS + 2 * S);      // warp 0's hv[0]
+  int running = 0;
+  if (lane < 2 * W) {
+    int* fl = flags_of(lane >> 1);
+    const int kk = lane & 1;
+    if (fl[kk] == NB::RUN) {
+      double* q = region_R(lane >> 1) + kk * kMat;
+      double d[S], e[S];
+#pragma unroll
+      for (int i = 0; i < S; ++i) { d[i] = q[i]; e[i] = q[S + i]; }
+      int l = (int)q[2 * S], iter = (int)q[2 * S + 1];
+      double dl = q[2 * S + 2], dl1 = q[2 * S + 3], el = q[2 * S + 4];
+      double2* rec = reinterpret_cast<double2*>(region_T(lane >> 1, kk));
+      int* rec_l = reinterpret_cast<int*>(region_T(lane >> 1, kk) + 2 * K * S);
+      int nsw = 0;
+      const int st = ql_run_recorded<S>(d, e, l, iter, dl, dl1, el, K, rec, rec_l, nsw);
+#pragma unroll
+      for (int i = 0; i < S; ++i) { q[i] = d[i]; q[S + i] = e[i]; }
+      q[2 * S] = (double)l; q[2 * S + 1] = (double)iter; q[2 * S + 2] = dl; q[2 * S + 3] = dl1; q[2 * S + 4] = el;
+      fl[2 + kk] = nsw;
+      fl[kk] = st == 0 ? NB::RUN : st == 1 ? NB::DONE : NB::FAILED;
+      running = st == 0;
+    } else {
+      fl[2 + kk] = 0;
+    }
+  }
+  const int any = __any_sync(kFull, running);
+  if (lane == 0) *all_done = !any;
+}
 
 // LIVE = false: participant without matrices.  Returns (per half-warp) whether its matrix was solved; then fd holds the
 // eigenvalues and fz the lane's row of V Q.
@@ -201,11 +250,13 @@ MFS_DEV bool nd_batched_ql(double* __restrict__ cta_base, const int warp, const 
   using NB = NdBatch<N>;
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS, W = nd_warps<N>(), K = NB::kSweeps, kMat = NB::kMat;
-  constexpr unsigned kFull = 0xffffffffu;
   static_assert(2 * W <= 32, "one lane per matrix");
   const int k = lane >> 4, r = lane & 15;
   auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::Z; };
-  auto region_T = [&](int w, int kk) { return cta_base + w * D::kDoubles + D::Z + SS + kk * SS; };
+  auto region_T = [&](int w, int kk) {       // 16-byte aligned (double2 records): Z + SS may be odd
+    double* t = cta_base + w * D::kDoubles + D::Z + SS + kk * SS;
+    return t + ((reinterpret_cast<uintptr_t>(t) >> 3) & 1);
+  };
   auto flags_of = [&](int w) { return reinterpret_cast<int*>(region_R(w) + 2 * kMat); };
   int* const all_done = reinterpret_cast<int*>(cta_base + D::Z + 5 * SS + SS + 2 * S);      // warp 0's hv[0]
   int* const my_flags = flags_of(warp);
@@ -223,35 +274,7 @@ MFS_DEV bool nd_batched_ql(double* __restrict__ cta_base, const int warp, const 
   }
   __syncthreads();
   for (;;) {
-    if (warp == 0) {
-      int running = 0;
-      if (lane < 2 * W) {
-        int* fl = flags_of(lane >> 1);
-        const int kk = lane & 1;
-        if (fl[kk] == NB::RUN) {
-          double* q = region_R(lane >> 1) + kk * kMat;
-          double d[S], e[S];
-#pragma unroll
-          for (int i = 0; i < S; ++i) { d[i] = q[i]; e[i] = q[S + i]; }
-          int l = (int)q[2 * S], iter = (int)q[2 * S + 1];
-          double dl = q[2 * S + 2], dl1 = q[2 * S + 3], el = q[2 * S + 4];
-          double2* rec = reinterpret_cast<double2*>(region_T(lane >> 1, kk));
-          int* rec_l = reinterpret_cast<int*>(region_T(lane >> 1, kk) + 2 * K * S);
-          int nsw = 0;
-          const int st = ql_run_recorded<S>(d, e, l, iter, dl, dl1, el, K, rec, rec_l, nsw);
-#pragma unroll
-          for (int i = 0; i < S; ++i) { q[i] = d[i]; q[S + i] = e[i]; }
-          q[2 * S] = (double)l; q[2 * S + 1] = (double)iter; q[2 * S + 2] = dl; q[2 * S + 3] = dl1; q[2 * S + 4] = el;
-          fl[2 + kk] = nsw;
-          fl[kk] = st == 0 ? NB::RUN : st == 1 ? NB::DONE : NB::FAILED;
-          running = st == 0;
-        } else {
-          fl[2 + kk] = 0;
-        }
-      }
-      const int any = __any_sync(kFull, running);
-      if (lane == 0) *all_done = !any;
-    }
+    if (warp == 0) nd_batched_scalar_phase<N>(cta_base, lane);
     __syncthreads();
     if (LIVE) {
       const int nsw = my_flags[2 + k];
@@ -530,7 +553,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
         double fd[S], fe[S], fz[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) { fd[i] = qd[i]; fe[i] = qe[i]; fz[i] = z[i]; }
-        bool ok = tridiag_ql_first_row<S, false, (S <= 16 ? MFS_ND_CASCADE_SMALL : MFS_ND_CASCADE_LARGE)>(fd, fe, fz);
+        bool ok = tridiag_ql_first_row<S, false, (S <= 16 ? MFS_ND_CASCADE_SMALL : MFS_ND_CASCADE_LARGE), (S >= MFS_ND_QL_CHAIN7_MIN_S)>(fd, fe, fz);
         double chk = 0.0;
 #pragma unroll
         for (int i = 0; i < S; ++i) chk += fabs(fd[i]);          // identical in every lane of the group
