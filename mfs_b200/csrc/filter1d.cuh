@@ -477,6 +477,17 @@ MFS_DEV double2 mean_var(const double (&ms)[2 * N], double mean, double scale) {
   return make_double2(mean, scale * scale * ms[2]);
 }
 
+// One CTA barrier per time step?  Measured on B200 (profiles/r2_ab_1d_step_barrier.log): it pays where the code of a step is
+// large -- the Normal family (+6.5 % at N = 7), N >= 12 (+5.5 %) -- and costs 0.5-4 % for the small Benes instances.
+template <int N, int KIND>
+constexpr bool step_barrier() {
+#ifdef MFS_1D_STEP_BARRIER
+  return MFS_1D_STEP_BARRIER != 0;
+#else
+  return KIND == KIND_NORMAL || N >= 10;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 template <int N, int MODE, int KIND, int MEAS>
 __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const mfs_filter1d_args P, const SegInfo G) {
@@ -484,8 +495,21 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   double* const sm = smem_tile + threadIdx.x;
   const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t n_active = G.count_in ? (int64_t)__ldg(G.count_in) : P.B;
-  if (slot >= n_active) return;
-  const int64_t b = G.idx_in ? (int64_t)__ldg(G.idx_in + slot) : slot;
+  // One CTA barrier per time step (step_barrier<N, KIND>()): keeps the CTA's four warps on the same code, so that one
+  // instruction fetch serves all of them -- the 2-D kernel's lever (filter_nd.cuh), which pays here where the step's code
+  // is large.  Every thread of a CTA that has at least one filter then runs the whole time loop; `alive` says whether it
+  // still has work (a thread beyond the batch reads the last filter's inputs and writes nothing).
+  constexpr bool kBar = step_barrier<N, KIND>();
+  bool present = true;
+  int64_t slot_rd = slot;
+  if constexpr (kBar) {
+    if ((int64_t)blockIdx.x * kBlock >= n_active) return;
+    present = slot < n_active;
+    slot_rd = present ? slot : n_active - 1;
+  } else {
+    if (slot >= n_active) return;
+  }
+  const int64_t b = G.idx_in ? (int64_t)__ldg(G.idx_in + slot_rd) : slot_rd;
   const double* park_in = G.state_in ? G.state_in + b * seg_state_doubles<N>() : nullptr;
   double* park_out = G.state_out ? G.state_out + b * seg_state_doubles<N>() : nullptr;
 
@@ -534,9 +558,15 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
   double* scale_out = P.scale_out ? P.scale_out + b * P.aux_stride_b : nullptr;
 
   int64_t t = G.t0;
-  if (status < 0 && t < G.t1) {
-    double y_next = load_y(P.ys, P.ys_dtype, ys_off + t * P.ys_stride_t);
+  bool alive = present && status < 0;
+  int64_t t_stop = G.t0;                 // kBar: where this thread's filter stopped (NaN from there on)
+  if ((kBar || alive) && t < G.t1) {
+    double y_next = alive ? load_y(P.ys, P.ys_dtype, ys_off + t * P.ys_stride_t) : 0.0;
     for (; t < G.t1; ++t) {
+      if constexpr (kBar) {
+        __syncthreads();
+        if (!alive) continue;
+      }
       const double y = y_next;
       if (t + 1 < G.t1) y_next = load_y(P.ys, P.ys_dtype, ys_off + (t + 1) * P.ys_stride_t);
 
@@ -584,7 +614,16 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
           nell -= log(cc);
         }
       }
-      if (!ok) { status = (int)(P.t_offset + t); break; }
+      if (!ok) {
+        status = (int)(P.t_offset + t);
+        if constexpr (kBar) {
+          alive = false;
+          t_stop = t;
+          continue;
+        } else {
+          break;
+        }
+      }
 
       if (P.out_mode == MFS_OUT_FULL) {
         double* o = ms_out + t * P.ms_stride_t;
@@ -598,6 +637,10 @@ __global__ void __launch_bounds__(kBlock, min_blocks<N>()) filter1d_kernel(const
     }
   }
 
+  if constexpr (kBar) {
+    if (!present) return;
+    if (status >= 0) t = t_stop;
+  }
   if (status >= 0) {
     // JAX semantics: once the Cholesky fails everything downstream is NaN until the end of the scan.
     const double qnan = nan("");

@@ -349,7 +349,16 @@ MFS_DEV S measurement_pdf_t(int meas_id, double y, double lgam, const S& x, cons
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef MFS_GRAD_MIN_BLOCKS
-#define MFS_GRAD_MIN_BLOCKS 4
+#define MFS_GRAD_MIN_BLOCKS 2
+#endif
+// threads per CTA, and one CTA barrier per time step (the value kernel's step_barrier, filter1d.cuh): with the barrier the
+// CTA's warps fetch the same code at the same time.  Measured (profiles/r2_ab_1d_step_barrier.log, N = 7): 64 threads x 4
+// CTAs without the barrier 7.58e8 steps/s, with it 8.26e8, 128 threads x 2 CTAs with it 8.37e8 (+10 %).
+#ifndef MFS_GRAD_BLOCK
+#define MFS_GRAD_BLOCK 128
+#endif
+#ifndef MFS_GRAD_STEP_BARRIER
+#define MFS_GRAD_STEP_BARRIER 1
 #endif
 #ifdef MFS_GRAD_UNROLL_NODES
 #define MFS_NODE_LOOP _Pragma("unroll")
@@ -490,10 +499,18 @@ MFS_DEV bool quadrature_t(const S (&ms)[2 * N], const S& mean, S (&w)[N], S (&x)
 #endif
 
 template <int N, int P>
-__global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(const mfs_filter1d_args A, const GradInfo G) {
+__global__ void __launch_bounds__(MFS_GRAD_BLOCK, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(const mfs_filter1d_args A, const GradInfo G) {
   using S = Dual<P>;
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  constexpr bool kBar = MFS_GRAD_STEP_BARRIER != 0;
+  const int64_t b_own = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool present = true;
+  if constexpr (kBar) {
+    if ((int64_t)blockIdx.x * blockDim.x >= A.B) return;
+    present = b_own < A.B;        // a thread beyond the batch runs the loop's barriers on the last filter's inputs, writes nothing
+  } else {
+    if (b_own >= A.B) return;
+  }
+  const int64_t b = present ? b_own : A.B - 1;
   const bool central = A.mode == MFS_MODE_CENTRAL;
   const bool normal_family = A.trans_id != MFS_TRANS_TME;
   const double c = 0.5 * A.dispersion * A.dispersion;
@@ -519,8 +536,13 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
   int32_t status = -1;
   bool ok = MFS_GRAD_QUADRATURE(ms, mean, w, x);   // filtering.py:78 / :145 at k = 0
   if (!ok) status = 0;
+  if (!present) ok = false;
 
-  for (int64_t t = 0; t < A.T && ok; ++t) {
+  for (int64_t t = 0; t < A.T && (kBar || ok); ++t) {
+    if constexpr (kBar) {
+      __syncthreads();
+      if (!ok) continue;
+    }
     const double y = load_y(A.ys, A.ys_dtype, b * A.ys_stride_b + t * A.ys_stride_t);
     // ---- prediction (filtering.py:78-79 / :145-148)
     // The loops over the N atoms are ROLLED (MFS_NODE_LOOP): w, x, mu, var, g are indexed dynamically and live in
@@ -596,7 +618,10 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
     }
     // ---- update (filtering.py:81-86 / :150-158)
     ok = MFS_GRAD_QUADRATURE(ms, central ? mean : make_dual<P>(0.0), w, x);
-    if (!ok) { status = (int32_t)t; break; }
+    if (!ok) {
+      status = (int32_t)t;
+      if constexpr (kBar) continue; else break;
+    }
     const double lgam = (A.meas_id == MFS_MEAS_POISSON_SOFTPLUS) ? log_factorial(y) : 0.0;
     S cc = make_dual<P>(0.0);
     MFS_NODE_LOOP
@@ -636,6 +661,7 @@ __global__ void __launch_bounds__(64, MFS_GRAD_MIN_BLOCKS) filter1d_grad_kernel(
       }
     }
   }
+  if (!present) return;
   const double qnan = nan("");
   A.nell_out[b] = ok ? nell.v : qnan;
 #pragma unroll

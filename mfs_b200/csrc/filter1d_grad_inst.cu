@@ -12,8 +12,8 @@ cudaError_t launch_filter1d_grad(const mfs_filter1d_args& a, const GradInfo& g, 
 
 template <>
 cudaError_t launch_filter1d_grad<MFS_N>(const mfs_filter1d_args& a, const GradInfo& g, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((a.B + 63) / 64);
-  filter1d_grad_kernel<MFS_N, 2><<<grid, 64, 0, stream>>>(a, g);
+  const unsigned grid = (unsigned)((a.B + MFS_GRAD_BLOCK - 1) / MFS_GRAD_BLOCK);
+  filter1d_grad_kernel<MFS_N, 2><<<grid, MFS_GRAD_BLOCK, 0, stream>>>(a, g);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ from mfs_b200.simulate import simulate_1d
 
 tag = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith('--') else os.environ.get('MFS_B200_LIB', 'default')
 quick = '--quick' in sys.argv
+sweep = '--sweep' in sys.argv      # every order N = 2..15 at T = 100 (raw Benes) + the Normal / Poisson instance at a few N
 
 
 def timed(fn, reps=3):
@@ -65,6 +66,12 @@ def well(N, B, T):
           f'diverged {(out[-1] >= 0).double().mean().item():.3f}', flush=True)
 
 
+if sweep:
+    for n in range(2, 16):
+        benes(n, 909312 if n <= 4 else 454656 if n <= 8 else 227328, 100, 'raw', 'none')
+    for n in (3, 5, 7, 9, 12):
+        well(n, 75776 * 4 if n <= 7 else 75776 * 2, 200)
+    sys.exit(0)
 benes(8, 454656, 100, 'raw', 'none')
 benes(8, 1000000, 1000, 'raw', 'full')
 well(7, 75776 * 4, 1000)

@@ -23,7 +23,8 @@ for N in range(2, 16):
     fam = sde_cond_moments_tme(drift, disp, dt, 3)
     rates = []
     for mode in ('raw', 'central'):
-        for _ in range(2):
+        best = None
+        for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if mode == 'raw':
@@ -32,7 +33,9 @@ for N in range(2, 16):
                 out = moment_filter_cms(fam[1], fam[3], pmf, ic.cms, ic.mean, ys, history='none', return_status=True)
             e1.record()
             torch.cuda.synchronize()
-        rates.append(B * T / (e0.elapsed_time(e1) * 1e-3))
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best     # N = 2 runs 3 ms: host jitter shows
+        rates.append(B * T / (best * 1e-3))
         if mode == 'raw':
             div = float((out[-1] >= 0).double().mean())
     W = (2 / 3) * N ** 3 + 85 * N ** 2 + 130 * N + 30 - 20 * N * (N + 1)
