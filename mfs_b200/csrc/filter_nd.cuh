@@ -152,9 +152,27 @@ struct NdDims {
   static constexpr int Z = N * (2 * N + 1);        // number of moments, |n| <= 2N-1
   static constexpr int M = 2 * N;                  // orders 0..2N-1 per dimension
   static constexpr int SS = S * S;
-  // per-warp shared memory in doubles: ms, R, T[2], V[2], wts, lam[2], Householder v[2] / w[2]
-  static constexpr int kDoubles = Z + 5 * SS + SS + 2 * S + 4 * S;
-  static constexpr int kTabInts = 3 * SS;          // per CTA: gather table
+  // Per-warp shared memory in doubles: ms | R | T[kNumT] | V[2] | (wts) | lam[2] | Householder v[2], w[2].
+  // Round 2: the weights live in the R region (the Cholesky factor is dead once stage B is done, the weights are dead
+  // before the next call's stage A writes the factor), and the two-pass sizes (S > 16: one matrix at a time) share one
+  // transpose buffer.  N = 7: 39.8 -> 27.3 KB per filter, which with the byte-wide gather table makes room for a second
+  // CTA per SM (profiles/r2_ab_nd_smem.log); -DMFS_ND_NO_SMEM_ALIAS restores the round-1 layout.
+#ifdef MFS_ND_NO_SMEM_ALIAS
+  static constexpr bool kAlias = false;
+#else
+  static constexpr bool kAlias = true;
+#endif
+  static constexpr int kNumT = (S <= 16 || !kAlias) ? 2 : 1;
+  static constexpr int kOffR = Z;
+  static constexpr int kOffT = kOffR + SS;
+  static constexpr int kOffV = kOffT + kNumT * SS;
+  static constexpr int kOffW = kAlias ? kOffR : kOffV + 2 * SS;
+  static constexpr int kOffLam = kOffV + 2 * SS + (kAlias ? 0 : SS);
+  static constexpr int kOffHv = kOffLam + 2 * S;
+  static constexpr int kOffHw = kOffHv + 2 * S;
+  static constexpr int kDoubles = kOffHw + 2 * S;
+  static constexpr int kScratch = (kNumT + 2) * SS;        // T and V: idle between quadratures (warp_reduce_moments)
+  static constexpr int kTabBytes = (3 * SS + 7) / 8 * 8;   // per CTA: the (3, S, S) gather table, one byte per entry (< Z <= 105)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -205,13 +223,13 @@ __device__ __noinline__ void nd_batched_scalar_phase(double* __restrict__ cta_ba
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS, W = nd_warps<N>(), K = NB::kSweeps, kMat = NB::kMat;
   constexpr unsigned kFull = 0xffffffffu;
-  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::Z; };
+  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::kOffR; };
   auto region_T = [&](int w, int kk) {       // 16-byte aligned (double2 records): Z + SS may be odd
-    double* t = cta_base + w * D::kDoubles + D::Z + SS + kk * SS;
+    double* t = cta_base + w * D::kDoubles + D::kOffT + kk * SS;
     return t + ((reinterpret_cast<uintptr_t>(t) >> 3) & 1);
   };
   auto flags_of = [&](int w) { return reinterpret_cast<int*>(region_R(w) + 2 * kMat); };
-  int* const all_done = reinterpret_cast<int*>(cta_base + D::Z + 5 * SS + SS + 2 * S);      // warp 0's hv[0]
+  int* const all_done = reinterpret_cast<int*>(cta_base + D::kOffHv);      // warp 0's hv[0]
   int running = 0;
   if (lane < 2 * W) {
     int* fl = flags_of(lane >> 1);
@@ -252,13 +270,13 @@ MFS_DEV bool nd_batched_ql(double* __restrict__ cta_base, const int warp, const 
   constexpr int S = D::S, SS = D::SS, W = nd_warps<N>(), K = NB::kSweeps, kMat = NB::kMat;
   static_assert(2 * W <= 32, "one lane per matrix");
   const int k = lane >> 4, r = lane & 15;
-  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::Z; };
+  auto region_R = [&](int w) { return cta_base + w * D::kDoubles + D::kOffR; };
   auto region_T = [&](int w, int kk) {       // 16-byte aligned (double2 records): Z + SS may be odd
-    double* t = cta_base + w * D::kDoubles + D::Z + SS + kk * SS;
+    double* t = cta_base + w * D::kDoubles + D::kOffT + kk * SS;
     return t + ((reinterpret_cast<uintptr_t>(t) >> 3) & 1);
   };
   auto flags_of = [&](int w) { return reinterpret_cast<int*>(region_R(w) + 2 * kMat); };
-  int* const all_done = reinterpret_cast<int*>(cta_base + D::Z + 5 * SS + SS + 2 * S);      // warp 0's hv[0]
+  int* const all_done = reinterpret_cast<int*>(cta_base + D::kOffHv);      // warp 0's hv[0]
   int* const my_flags = flags_of(warp);
   if (LIVE) {
     if (r == 0) {
@@ -317,19 +335,19 @@ MFS_DEV void nd_batched_ql_idle(double* __restrict__ cta_base, const int warp, c
 // BATCH: stage D through the CTA-batched protocol (nd_batched_ql): EVERY warp of the CTA must then make the same calls
 // (a warp without a live filter calls nd_batched_ql_idle instead); cta_base = start of the CTA's shared memory.
 template <int N, bool BATCH = false>
-__device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ tab, int lane, int stable,
+__device__ __noinline__ int quadrature_nd(double* sm, const unsigned char* __restrict__ tab, int lane, int stable,
                                           double* cta_base = nullptr, int warp = 0) {   // one copy, two call sites
   using D = NdDims<N>;
   constexpr int S = D::S, SS = D::SS;
   constexpr unsigned kFull = 0xffffffffu;
   double* ms = sm;
-  double* R = ms + D::Z;       // [S][S] Cholesky factor
-  double* T = R + SS;          // [2][S][S] transpose buffers
-  double* V = T + 2 * SS;      // [2][S][S]
-  double* wts = V + 2 * SS;
-  double* lam = wts + SS;      // [2][S]
-  double* hv = lam + 2 * S;    // [2][S] Householder v
-  double* hw = hv + 2 * S;     // [2][S] Householder w
+  double* R = sm + D::kOffR;      // [S][S] Cholesky factor
+  double* T = sm + D::kOffT;      // [kNumT][S][S] transpose buffers
+  double* V = sm + D::kOffV;      // [2][S][S]
+  double* wts = sm + D::kOffW;    // [S][S] (the R region: see NdDims)
+  double* lam = sm + D::kOffLam;  // [2][S]
+  double* hv = sm + D::kOffHv;    // [2][S] Householder v
+  double* hw = sm + D::kOffHw;    // [2][S] Householder w
 
   // ---- A: Cholesky (lower).  Failure <=> a pivot is not > 0 (jax: NaN-filled factor).
   double rdi[S];               // 1 / R[j][j], identical in every lane
@@ -400,7 +418,7 @@ __device__ __noinline__ int quadrature_nd(double* sm, const int* __restrict__ ta
     const int gbase = lane & ~(LPM - 1);
     const bool act = r < S;
     const int cc = act ? r : 0;
-    double* Tk = T + k * SS;
+    double* Tk = T + (D::kNumT == 2 ? k : 0) * SS;
     double* v = hv + k * S;
     double* w = hw + k * S;
     auto group_sum = [&](double x) {
@@ -779,8 +797,9 @@ MFS_DEV void accumulate_tme_moments(double wgt, double dl1, double dl2, const do
 // instead of Z unrolled butterfly reductions (the latter were 60 % of the kernel's code size).
 template <int N>
 MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scratch, double* ms, double scale, int lane) {
-  constexpr int Z = NdDims<N>::Z, SS = NdDims<N>::SS;
-  constexpr int BS = (4 * SS / 32 > 32) ? 32 : (4 * SS / 32 < 1 ? 1 : 4 * SS / 32);   // moments per batch
+  constexpr int Z = NdDims<N>::Z;
+  constexpr int kScr = NdDims<N>::kScratch;
+  constexpr int BS = (kScr / 32 > 32) ? 32 : (kScr / 32 < 1 ? 1 : kScr / 32);   // moments per batch
 #pragma unroll
   for (int p0 = 0; p0 < Z; p0 += BS) {
 #pragma unroll
@@ -802,7 +821,7 @@ MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scra
 #ifdef MFS_ND_MIN_BLOCKS
 template <int N> constexpr int nd_min_blocks() { return MFS_ND_MIN_BLOCKS; }
 #else
-template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N <= 6 ? 2 : 1; }
+template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : 2; }
 #endif
 template <int N>
 __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {
@@ -813,8 +832,8 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * kNdWarps + warp;
   // the (3, S, S) gather table, shared by the CTA's warps
-  int* tab = reinterpret_cast<int*>(smem_all + kNdWarps * D::kDoubles);
-  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = __ldg(P.inds + e);
+  unsigned char* tab = reinterpret_cast<unsigned char*>(smem_all + kNdWarps * D::kDoubles);
+  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = (unsigned char)__ldg(P.inds + e);
   __syncthreads();
   // Phase barriers (nd_step_barriers<N>() per time step): the CTA's warps are independent filters, but left alone they
   // drift apart (data-dependent sweep counts) and each streams the kernel's 250+ KB of unrolled code through the
@@ -851,9 +870,9 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter
   }
   double* sm = smem_all + warp * D::kDoubles;
   double* ms = sm;
-  double* scratch = sm + Z + SS;      // T and V of the quadrature (4 S^2 doubles), idle between quadratures
-  double* wts = sm + Z + 5 * SS;
-  double* lam = wts + SS;
+  double* scratch = sm + D::kOffT;    // T and V of the quadrature (NdDims::kScratch doubles), idle between quadratures
+  double* wts = sm + D::kOffW;
+  double* lam = sm + D::kOffLam;
 
   for (int e = lane; e < Z; e += 32) ms[e] = __ldg(P.ms0 + b * P.ms0_stride + e);
   double mean1 = 0.0, mean2 = 0.0;
@@ -1039,13 +1058,13 @@ __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) quadra
   extern __shared__ double smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * kNdWarps + warp;
-  int* tab = reinterpret_cast<int*>(smem_all + kNdWarps * D::kDoubles);
-  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = __ldg(P.inds + e);
+  unsigned char* tab = reinterpret_cast<unsigned char*>(smem_all + kNdWarps * D::kDoubles);
+  for (int e = threadIdx.x; e < 3 * SS; e += kNdWarps * 32) tab[e] = (unsigned char)__ldg(P.inds + e);
   __syncthreads();
   if (b >= P.B) return;
   double* sm = smem_all + warp * D::kDoubles;
-  double* wts = sm + Z + 5 * SS;
-  double* lam = wts + SS;
+  double* wts = sm + D::kOffW;
+  double* lam = sm + D::kOffLam;
   for (int e = lane; e < Z; e += 32) sm[e] = __ldg(P.ms + b * Z + e);
   __syncwarp();
   const int why = quadrature_nd<N>(sm, tab, lane, P.stable);

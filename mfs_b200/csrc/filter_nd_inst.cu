@@ -20,7 +20,7 @@ template <int N>
 cudaError_t launch_filter_nd(const NdArgs& a, cudaStream_t stream) {
   using D = NdDims<N>;
   constexpr int kNdWarps = nd_warps<N>();
-  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
+  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + D::kTabBytes;
   static bool configured[64] = {};
   if (cudaError_t e = opt_in_smem(filter_nd_kernel<N>, configured, smem)) return e;
   const unsigned grid = (unsigned)((a.B + kNdWarps - 1) / kNdWarps);
@@ -32,7 +32,7 @@ template <int N>
 cudaError_t launch_quadrature_nd(const NdQuadArgs& a, cudaStream_t stream) {
   using D = NdDims<N>;
   constexpr int kNdWarps = nd_warps<N>();
-  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + sizeof(int) * D::kTabInts;
+  const size_t smem = sizeof(double) * kNdWarps * D::kDoubles + D::kTabBytes;
   static bool configured[64] = {};
   if (cudaError_t e = opt_in_smem(quadrature_nd_kernel<N>, configured, smem)) return e;
   const unsigned grid = (unsigned)((a.B + kNdWarps - 1) / kNdWarps);
