@@ -19,11 +19,14 @@
 namespace mfs {
 
 // warps (= filters) per CTA
+#ifndef MFS_ND_WARPS_LARGE
+#define MFS_ND_WARPS_LARGE 4    // N >= 6 (255 registers: 8 warps per SM): 4 = two CTAs, 8 = one
+#endif
 template <int N> constexpr int nd_warps() {
 #ifdef MFS_ND_WARPS
-  return N <= 5 ? MFS_ND_WARPS : 4;
+  return N <= 5 ? MFS_ND_WARPS : MFS_ND_WARPS_LARGE;
 #else
-  return N == 5 ? 8 : 4;      // N = 5: 2 CTAs x 8 warps at 128 registers (profiles/r2_ab_nd_barrier.log)
+  return N == 5 ? 8 : N >= 6 ? MFS_ND_WARPS_LARGE : 4;      // N = 5: 2 CTAs x 8 warps at 128 registers (profiles/r2_ab_nd_barrier.log)
 #endif
 }
 // deflation cascade of the register QL (quadrature.cuh): 0 = inlined per exit, 1 = shared guarded levels, 2 = shared switch
@@ -821,7 +824,7 @@ MFS_DEV void warp_reduce_moments(const double (&acc)[NdDims<N>::Z], double* scra
 #ifdef MFS_ND_MIN_BLOCKS
 template <int N> constexpr int nd_min_blocks() { return MFS_ND_MIN_BLOCKS; }
 #else
-template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : 2; }
+template <int N> constexpr int nd_min_blocks() { return N <= 4 ? 4 : N == 5 ? 2 : 8 / nd_warps<N>(); }
 #endif
 template <int N>
 __global__ void __launch_bounds__(nd_warps<N>() * 32, nd_min_blocks<N>()) filter_nd_kernel(const NdArgs P) {
