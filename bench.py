@@ -104,6 +104,32 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs next to its GPU (NVML's ideal affinity) while the pinned host buffers of the e2e
+    legs are allocated and filled, so that on a two-socket host they land on the GPU's own NUMA node instead of wherever
+    the rank happened to be scheduled.  Returns (previous affinity, number of CPUs bound to) or (None, 0) if NVML or the
+    affinity call is unavailable; the caller restores the previous affinity afterwards."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(props.uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        local = cpus & prev
+        if not local or local == prev:
+            return None, len(prev)
+        os.sched_setaffinity(0, local)
+        return prev, len(local)
+    except Exception:
+        return None, 0
+
+
 def cpu_baseline(N, T, target_seconds=15., threads=0, seed=666 + 1):
     """Time the C oracle on a bounded sample of the same workload.  Returns (steps/s, cores, sample string)."""
     from oracle import c_oracle
@@ -551,6 +577,7 @@ def main():
                     'd2h_bytes_per_step': int(d2h), 'batch_per_gpu': Be, 'history': history,
                     'pcie_gb_per_s_per_gpu': gbs}
 
+        prev_affinity, numa_cpus = bind_to_gpu_numa(local_rank)
         # full history: 16.8 GB of pinned host memory per 131072 filters and per rank
         Be_full = min(B, args.e2e_batch if world <= 2 else max(32768, args.e2e_batch // 4))
         e2e_modes['full'] = e2e_leg('full', Be_full)
@@ -560,7 +587,12 @@ def main():
             torch.cuda.empty_cache()
             e2e_modes['meanvar'] = e2e_leg('meanvar', min(B, 2 * args.e2e_batch), chunk=148 * 4 * 128)
         e2e_modes['none'] = e2e_leg('none', B)
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)
         e2e = dict(e2e_modes['full'])
+        e2e['host_numa_binding'] = (f'rank bound to the {numa_cpus} CPUs NVML lists as local to its GPU while the pinned '
+                                    f'buffers were allocated' if prev_affinity is not None else
+                                    'none (NVML affinity unavailable, or all of this process\'s CPUs are local to the GPU)')
         e2e['note'] = ('pinned host buffers, chunked H2D->kernel->D2H pipeline inside mfs_filter_1d_host; the full moment '
                        'history (the reference\'s return value) is PCIe-bound at 128 B per filter-step; see e2e_modes for '
                        'the (mean, variance) history and the nell-only objective through the same call')
