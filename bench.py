@@ -309,7 +309,19 @@ def secondary_legs(rank, world, device_index, fp64_peak, scale=1.0, single_gpu_e
                                        'peak_source': 'measured live: mfs_dmma_peak (DMMA m8n8k4 micro-benchmark)'},
                           'max_abs_mass_error': float((mass - 1.).abs().max()),
                           'finite_nell_frac': total(float(torch.isfinite(nell_g).sum())) / (world * Bg)}
-    del ysg, pdf
+    # the same job with the operator's 100th power formed once (power_operator=True: one contraction per time step)
+    ms_p, (pdf_p, nell_p) = timed(lambda: brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip,
+                                                             xs, ysg, dtb, integration_steps=steps, pred_method='chapman-tme-3',
+                                                             history='last', return_nell=True, power_operator=True))
+    scale_p = pdf.abs().amax(dim=-1, keepdim=True)
+    out['grid_filter']['power_operator'] = {
+        'value': world * Bg * Tg / (ms_p * 1e-3), 'ms': ms_p, 'speedup_over_literal': ms / ms_p,
+        'max_rel_density_diff_vs_literal': float(((pdf_p - pdf).abs() / scale_p).max()),
+        'max_rel_nell_diff_vs_literal': float(((nell_p - nell_g).abs() / nell_g.abs()).max()),
+        'note': 'opt-in (MFS_BF_FLAG_POWER_OPERATOR): the sub-steps of a time step apply the same linear operator, so its '
+                f'{steps}th power is formed once per call by binary powering on the DMMA GEMM and every time step is one '
+                'contraction; same mathematics, different order of summation'}
+    del ysg, pdf, pdf_p
     torch.cuda.empty_cache()
     if not (single_gpu_extras and world == 1):
         return out

@@ -194,6 +194,11 @@ int mfs_filter_nd(const mfs_filternd_args* a, void* stream);
  * Drift functor + constant dispersion as in mfs_filter1d_args; trans_params are shared by all filters (one operator).
  * Device pointers; the caller owns the workspace (size from mfs_brute_force_workspace_bytes). */
 enum { MFS_BF_CHAPMAN_EULER = 0, MFS_BF_CHAPMAN_TME = 1, MFS_BF_KOLMOGOROV = 2 };
+/* mfs_brute_force_args.flags.  POWER_OPERATOR ('chapman' methods, integration_steps > 1): the sub-steps of a time step
+ * apply the same linear operator (brute_force.py:115-122), so the k-th power of the operator is formed once per call by
+ * binary powering on the FP64 tensor-core GEMM and every time step is ONE contraction instead of k.  Same mathematics,
+ * different rounding (associativity; all terms are non-negative: relative differences ~1e-13) -- hence opt-in. */
+enum { MFS_BF_FLAG_POWER_OPERATOR = 1 };
 
 typedef struct mfs_brute_force_args {
   int32_t abi_version;
@@ -216,15 +221,16 @@ typedef struct mfs_brute_force_args {
   const void* ys;             /* y[b][t] at ys + b*ys_stride_b + t*ys_stride_t */
   int64_t ys_stride_b, ys_stride_t;
   int32_t out_mode;           /* MFS_OUT_FULL: pdfs_out[B][T][n]; MFS_OUT_LAST: pdfs_out[B][n] */
-  int32_t reserved0;
+  int32_t flags;              /* MFS_BF_FLAG_* (0: the reference's literal recursion) */
   double* pdfs_out;
   double* nell_out;           /* optional [B]: -sum_t log trapz(p(y_t|x) p(x|y_{1:t-1})) (by-product; may be NULL) */
   void* workspace;
   int64_t workspace_bytes;
 } mfs_brute_force_args;
 
-/* Workspace size in bytes for mfs_brute_force (-1 for invalid arguments). */
+/* Workspace size in bytes for mfs_brute_force (-1 for invalid arguments); _ex: for a call with the given flags. */
 int64_t mfs_brute_force_workspace_bytes(int32_t n_grid, int64_t B, int32_t pred_method);
+int64_t mfs_brute_force_workspace_bytes_ex(int32_t n_grid, int64_t B, int32_t pred_method, int32_t flags);
 
 /* Enqueue the grid filter on `stream`.  Replaces jax.jit(brute_force_filter)(grid, ys) per trajectory
  * (dardel/benes_bernoulli/brute_force.py:51-55, 74). */

@@ -78,13 +78,14 @@ class BruteForceArgs(ctypes.Structure):
         ('trans_params', ctypes.c_void_p), ('meas_params', ctypes.c_void_p), ('meas_param_stride', ctypes.c_int64),
         ('xs', ctypes.c_void_p), ('init_ps', ctypes.c_void_p), ('init_ps_stride', ctypes.c_int64),
         ('ys', ctypes.c_void_p), ('ys_stride_b', ctypes.c_int64), ('ys_stride_t', ctypes.c_int64),
-        ('out_mode', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('out_mode', ctypes.c_int32), ('flags', ctypes.c_int32),
         ('pdfs_out', ctypes.c_void_p), ('nell_out', ctypes.c_void_p),
         ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
     ]
 
 
 BF_METHOD = {'chapman-euler': 0, 'chapman-tme': 1, 'kolmogorov': 2}
+BF_FLAG_POWER_OPERATOR = 1
 SIM_SCHEME = {'tme': 0, 'benes_exact': 1}
 SIM_MAX_COMPONENTS = 8
 
@@ -123,7 +124,7 @@ class SimulateLvArgs(ctypes.Structure):
 
 EXPORTS = ('mfs_abi_version', 'mfs_last_error', 'mfs_functor_lookup', 'mfs_filter_1d', 'mfs_filter_1d_host',
            'mfs_moment_quadrature_1d', 'mfs_launch_count', 'mfs_fp64_peak', 'mfs_release_cached_memory', 'mfs_filter_nd',
-           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd',
+           'mfs_brute_force', 'mfs_brute_force_workspace_bytes', 'mfs_brute_force_workspace_bytes_ex', 'mfs_dmma_peak', 'mfs_characteristic_fn_1d', 'mfs_filter_1d_workspace_bytes', 'mfs_moment_quadrature_nd',
            'mfs_simulate_1d', 'mfs_simulate_lv', 'mfs_filter_1d_grad', 'mfs_math_selftest')
 
 _lib = None
@@ -181,6 +182,8 @@ def lib() -> ctypes.CDLL:
         L.mfs_brute_force.restype = ctypes.c_int
         L.mfs_brute_force_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32]
         L.mfs_brute_force_workspace_bytes.restype = ctypes.c_int64
+        L.mfs_brute_force_workspace_bytes_ex.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]
+        L.mfs_brute_force_workspace_bytes_ex.restype = ctypes.c_int64
         L.mfs_dmma_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]
         L.mfs_dmma_peak.restype = ctypes.c_int

@@ -243,6 +243,22 @@ __global__ void bf_operator_kernel(int n, int Npad, int Kpad, const double* __re
   Pw[(int64_t)i * Kpad + j] = v;
 }
 
+// out[j][i] = in[i][j] for i, j < n (both [Npad][Kpad], padding left as it is: zero), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) bf_transpose_kernel(int n, int Kpad, const double* __restrict__ in, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;
+    tile[r][tx] = (i < n && j < n) ? in[(int64_t)i * Kpad + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + tx;
+    if (i < n && j < n) out[(int64_t)j * Kpad + i] = tile[tx][r];
+  }
+}
+
 // S[b][0..Kpad) <- init_ps[b][0..n), zero padding
 __global__ void bf_load_state_kernel(int64_t B, int n, int Kpad, const double* __restrict__ init_ps, int64_t stride,
                                      double* __restrict__ S) {
@@ -381,12 +397,19 @@ using namespace mfs;
 
 extern "C" {
 
-int64_t mfs_brute_force_workspace_bytes(int32_t n_grid, int64_t B, int32_t pred_method) {
+int64_t mfs_brute_force_workspace_bytes_ex(int32_t n_grid, int64_t B, int32_t pred_method, int32_t flags) {
   if (n_grid < 3 || B < 0) return -1;
   const int64_t Kpad = round_up(n_grid, BF_BK), Npad = round_up(n_grid, BF_BN);
   int64_t doubles = 2 * B * Kpad;                                 // two state buffers
-  if (pred_method != MFS_BF_KOLMOGOROV) doubles += Npad * Kpad + 3 * Kpad;   // Pw + column tables
+  if (pred_method != MFS_BF_KOLMOGOROV) {
+    doubles += Npad * Kpad + 3 * Kpad;                            // Pw + column tables
+    if (flags & MFS_BF_FLAG_POWER_OPERATOR) doubles += 5 * Npad * Kpad;      // P, Q = P^T, R ping-pong (see mfs_brute_force)
+  }
   return doubles * (int64_t)sizeof(double) + 256;
+}
+
+int64_t mfs_brute_force_workspace_bytes(int32_t n_grid, int64_t B, int32_t pred_method) {
+  return mfs_brute_force_workspace_bytes_ex(n_grid, B, pred_method, 0);
 }
 
 int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
@@ -405,7 +428,8 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   if (a->B == 0 || a->T == 0) return 0;
   if (!a->trans_params || !a->meas_params || !a->xs || !a->init_ps || !a->ys || !a->pdfs_out || !a->workspace)
     return fail("NULL pointer argument");
-  const int64_t need = mfs_brute_force_workspace_bytes(a->n_grid, a->B, a->pred_method);
+  if (a->flags & ~MFS_BF_FLAG_POWER_OPERATOR) return fail("unknown flags 0x%x", a->flags);
+  const int64_t need = mfs_brute_force_workspace_bytes_ex(a->n_grid, a->B, a->pred_method, a->flags);
   if (a->workspace_bytes < need) return fail("workspace too small: %lld < %lld bytes", (long long)a->workspace_bytes, (long long)need);
   if (a->B > 65535LL * BF_BM) return fail("B too large for one call (max %d)", 65535 * BF_BM);
   if (a->n_grid > 65408) return fail("n_grid too large (max 65408)");
@@ -448,6 +472,48 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   } else {
     if ((size_t)n * 5 * sizeof(double) > 200 * 1024) return fail("kolmogorov: n_grid=%d too large for shared memory (max %d)", n, 200 * 1024 / 40);
   }
+  // MFS_BF_FLAG_POWER_OPERATOR: the sub-steps of a time step apply the SAME linear operator (brute_force.py:115-122: the
+  // scan body does not depend on the sub-step), so  S (Pw^T)^k = S (Pw^k)^T : Pw^k by binary powering on the DMMA GEMM
+  // (2 log2 k + popcount k - 1 products of n x n matrices, once per call), then ONE contraction per time step instead
+  // of k.  The kernel computes X Y^T, so the pair (P, Q = P^T) is squared together: P P = gemm(P, Q), Q Q = gemm(Q, P).
+  const double* Pw_step = Pw;
+  int steps_eff = a->integration_steps;
+  if (chapman && (a->flags & MFS_BF_FLAG_POWER_OPERATOR) && a->integration_steps > 1) {
+    const int64_t mat = (int64_t)Npad * Kpad;
+    double* pool = col_cf + Kpad;
+    if (cudaMemsetAsync(pool, 0, sizeof(double) * 5 * mat, s) != cudaSuccess) return fail("cudaMemsetAsync failed");
+    double* Pb[2] = {Pw, pool};
+    double* Qb[2] = {pool + mat, pool + 2 * mat};
+    double* Rb[2] = {pool + 3 * mat, pool + 4 * mat};
+    const dim3 tgrid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
+    bf_transpose_kernel<<<tgrid, 256, 0, s>>>(n, Kpad, Pb[0], Qb[0]);
+    BF_CHECK();
+    launches += 1;
+    const dim3 pgrid((unsigned)(Npad / BF_BN), (unsigned)((n + BF_BM - 1) / BF_BM));
+    int pc = 0, rc = -1;
+    for (int k = a->integration_steps;;) {
+      if (k & 1) {
+        if (rc < 0) {
+          if (cudaMemcpyAsync(Rb[0], Pb[pc], sizeof(double) * mat, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return fail("cudaMemcpyAsync failed");
+          rc = 0;
+        } else {
+          bf_gemm_kernel<<<pgrid, BF_THREADS, BF_SMEM, s>>>(Rb[rc], Qb[pc], Rb[rc ^ 1], n, n, Kpad);     // R P
+          rc ^= 1;
+          launches += 1;
+        }
+      }
+      k >>= 1;
+      if (!k) break;
+      bf_gemm_kernel<<<pgrid, BF_THREADS, BF_SMEM, s>>>(Pb[pc], Qb[pc], Pb[pc ^ 1], n, n, Kpad);         // P P
+      bf_gemm_kernel<<<pgrid, BF_THREADS, BF_SMEM, s>>>(Qb[pc], Pb[pc], Qb[pc ^ 1], n, n, Kpad);         // Q Q = (P P)^T
+      pc ^= 1;
+      launches += 2;
+    }
+    BF_CHECK();
+    Pw_step = Rb[rc];
+    steps_eff = 1;
+  }
   bf_load_state_kernel<<<dim3((unsigned)B, (Kpad + 255) / 256), 256, 0, s>>>(B, n, Kpad, a->init_ps, a->init_ps_stride, S[0]);
   BF_CHECK();
   // the padding columns of the second buffer must be zero too (they meet the zero columns of Pw)
@@ -466,18 +532,18 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   for (int64_t t = 0; t < a->T; ++t) {
     if (chapman) {
       if (use_gemv) {
-        for (int k = 0; k < a->integration_steps; ++k) {
-          cudaError_t e = gemv_substep(S[cur], Pw, S[cur ^ 1], B, n, Kpad, sms, s, &launches);
+        for (int k = 0; k < steps_eff; ++k) {
+          cudaError_t e = gemv_substep(S[cur], Pw_step, S[cur ^ 1], B, n, Kpad, sms, s, &launches);
           if (e != cudaSuccess) return fail("brute-force launch failed: %s", cudaGetErrorString(e));
           cur ^= 1;
         }
       } else {
-        for (int k = 0; k < a->integration_steps; ++k) {
-          bf_gemm_kernel<<<ggrid, BF_THREADS, BF_SMEM, s>>>(S[cur], Pw, S[cur ^ 1], B, n, Kpad);
+        for (int k = 0; k < steps_eff; ++k) {
+          bf_gemm_kernel<<<ggrid, BF_THREADS, BF_SMEM, s>>>(S[cur], Pw_step, S[cur ^ 1], B, n, Kpad);
           cur ^= 1;
         }
         BF_CHECK();
-        launches += a->integration_steps;
+        launches += steps_eff;
       }
     } else {
       BfKolmogorovArgs k;

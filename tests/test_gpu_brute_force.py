@@ -165,3 +165,36 @@ def test_per_record_grids_like_the_reference_experiment():
         _close(out[k], ref)
     with pytest.raises(ValueError):
         brute_force_filter(benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip[0], xs, ys, dt)
+
+
+@pytest.mark.parametrize('steps', [2, 5, 12, 100])
+def test_power_operator_equals_the_literal_recursion(steps):
+    """power_operator=True: the k-th power of the sub-step operator by binary powering (k = 2 / 5 / 12 / 100: even, odd,
+    mixed bit patterns), one contraction per time step.  Equal to the literal k-sub-step recursion up to the order of
+    summation (all terms non-negative), on the GEMM path, the matrix-vector path and per-record grids; and to the NumPy
+    oracle of the reference's recursion."""
+    rng = np.random.Generator(np.random.PCG64(90 + steps))
+    n, B, T = 300, 150, 4
+    xs = np.linspace(-5., 5., n)
+    ys = (rng.random((B, T)) < 0.5).astype(np.uint8)
+    ip = 0.5 * O.norm_pdf(xs, -0.5, math.sqrt(0.05)) + 0.5 * O.norm_pdf(xs, 0.5, math.sqrt(0.05))
+    args = (benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip, xs)
+    kw = dict(integration_steps=steps, pred_method='chapman-tme-3', return_nell=True)
+    lit, nell_l = brute_force_filter(*args, ys, 1e-2, **kw)
+    pw, nell_p = brute_force_filter(*args, ys, 1e-2, power_operator=True, **kw)
+    _close(pw, lit.cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(nell_p.cpu().numpy(), nell_l.cpu().numpy(), rtol=1e-11)
+    one = brute_force_filter(*args, ys[3], 1e-2, power_operator=True, integration_steps=steps, pred_method='chapman-tme-3')
+    _close(one, lit[3].cpu().numpy(), rtol=1e-11)                      # matrix-vector path on the powered operator
+    ref = BF.brute_force_filter('benes', (), 1., lambda y, x: O.bernoulli_pmf(y, 1 / (1 + np.exp(-x ** 3 / 5))), ip, xs,
+                                ys[3], 1e-2, steps, 'chapman-tme-3')
+    _close(pw[3], ref, rtol=1e-11)
+    if steps == 5:                                                     # per-record grids, and 'kolmogorov' ignores the flag
+        xs2 = np.stack([np.linspace(-5. - 0.1 * k, 5. + 0.1 * k, n) for k in range(3)])
+        ip2 = np.stack([0.5 * O.norm_pdf(x, -0.5, math.sqrt(0.05)) + 0.5 * O.norm_pdf(x, 0.5, math.sqrt(0.05)) for x in xs2])
+        a2 = (benes_drift(), Dispersion(1.), bernoulli_logistic_cubic(5., 0.), ip2, xs2, ys[:3], 1e-2)
+        _close(brute_force_filter(*a2, integration_steps=steps, pred_method='chapman-euler', power_operator=True),
+               brute_force_filter(*a2, integration_steps=steps, pred_method='chapman-euler').cpu().numpy(), rtol=1e-11)
+        k1 = brute_force_filter(*args, ys[:2], 1e-3, integration_steps=20, pred_method='kolmogorov', power_operator=True)
+        k0 = brute_force_filter(*args, ys[:2], 1e-3, integration_steps=20, pred_method='kolmogorov')
+        assert torch.equal(k1, k0)
