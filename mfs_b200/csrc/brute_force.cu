@@ -474,8 +474,8 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
   }
   // MFS_BF_FLAG_POWER_OPERATOR: the sub-steps of a time step apply the SAME linear operator (brute_force.py:115-122: the
   // scan body does not depend on the sub-step), so  S (Pw^T)^k = S (Pw^k)^T : Pw^k by binary powering on the DMMA GEMM
-  // (2 log2 k + popcount k - 1 products of n x n matrices, once per call), then ONE contraction per time step instead
-  // of k.  The kernel computes X Y^T, so the pair (P, Q = P^T) is squared together: P P = gemm(P, Q), Q Q = gemm(Q, P).
+  // (log2 k + popcount k - 1 products of n x n matrices, once per call), then ONE contraction per time step instead
+  // of k.  The kernel computes X Y^T, so the transpose Q = P^T is kept next to P: P P = gemm(P, Q), R P = gemm(R, Q).
   const double* Pw_step = Pw;
   int steps_eff = a->integration_steps;
   if (chapman && (a->flags & MFS_BF_FLAG_POWER_OPERATOR) && a->integration_steps > 1) {
@@ -506,7 +506,7 @@ int mfs_brute_force(const mfs_brute_force_args* a, void* stream) {
       k >>= 1;
       if (!k) break;
       bf_gemm_kernel<<<pgrid, BF_THREADS, BF_SMEM, s>>>(Pb[pc], Qb[pc], Pb[pc ^ 1], n, n, Kpad);         // P P
-      bf_gemm_kernel<<<pgrid, BF_THREADS, BF_SMEM, s>>>(Qb[pc], Pb[pc], Qb[pc ^ 1], n, n, Kpad);         // Q Q = (P P)^T
+      bf_transpose_kernel<<<tgrid, 256, 0, s>>>(n, Kpad, Pb[pc ^ 1], Qb[pc ^ 1]);                       // Q = (P P)^T
       pc ^= 1;
       launches += 2;
     }
