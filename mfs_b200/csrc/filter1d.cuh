@@ -19,11 +19,13 @@ namespace mfs {
 constexpr int kBlock = MFS_BLOCK;
 
 // CTAs of 128 threads per SM that the register allocation must allow.  The step is a long dependent FP64 chain (QL
-// rotations), so resident warps are what hides the DFMA latency (profiles/r2_occupancy.md).
+// rotations), so resident warps are what hides the DFMA latency.  Since the quadrature atoms live in the shared-memory
+// tile (round 2), 128 registers are enough up to N = 14: 4 CTAs instead of 3 gives +6..8 % at N = 9..13, +2 % at N = 14,
+// -3 % at N = 15 (profiles/r2_ab_1d_occupancy_large_N.log).
 #ifdef MFS_MIN_BLOCKS
 template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 #else
-template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 8 ? 4 : 3; }
+template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 14 ? 4 : 3; }
 #endif
 
 // Carried filter state: [0, 2N) moments, [2N, 4N) what the next prediction starts from, mean, scale, nell, flag.
@@ -478,13 +480,14 @@ MFS_DEV double2 mean_var(const double (&ms)[2 * N], double mean, double scale) {
 }
 
 // One CTA barrier per time step?  Measured on B200 (profiles/r2_ab_1d_step_barrier.log): it pays where the code of a step is
-// large -- the Normal family (+6.5 % at N = 7), N >= 12 (+5.5 %) -- and costs 0.5-4 % for the small Benes instances.
+// large -- the Normal family (+6 % at N = 7, +6..13 % at N = 9, 12), Benes N = 9: +1 %, N = 10..14: +2..8 % at the shipped
+// 4 CTAs per SM -- and costs 0.5-4 % for the small Benes instances (N = 2: -29 %).
 template <int N, int KIND>
 constexpr bool step_barrier() {
 #ifdef MFS_1D_STEP_BARRIER
   return MFS_1D_STEP_BARRIER != 0;
 #else
-  return KIND == KIND_NORMAL || N >= 10;
+  return KIND == KIND_NORMAL || N >= 9;
 #endif
 }
 
