@@ -21,11 +21,14 @@ constexpr int kBlock = MFS_BLOCK;
 // CTAs of 128 threads per SM that the register allocation must allow.  The step is a long dependent FP64 chain (QL
 // rotations), so resident warps are what hides the DFMA latency.  Since the quadrature atoms live in the shared-memory
 // tile (round 2), 128 registers are enough up to N = 14: 4 CTAs instead of 3 gives +6..8 % at N = 9..13, +2 % at N = 14,
-// -3 % at N = 15 (profiles/r2_ab_1d_occupancy_large_N.log).
+// -3 % at N = 15 (profiles/r2_ab_1d_occupancy_large_N.log).  Re-measured with the final kernel (the QL with compile-time
+// positions and the rolled atom loops lowered the pressure further; profiles/r2_ab_1d_occupancy_small_N.log): 6 CTAs (80
+// registers) instead of 4 give +5 % at N = 8 -- +6 % on the headline case --, +4 % at N = 7; 5 CTAs +2 / +1 % at N = 9 / 10;
+// one more CTA than that costs 2..50 % everywhere (spills).
 #ifdef MFS_MIN_BLOCKS
 template <int N> constexpr int min_blocks() { return MFS_MIN_BLOCKS; }
 #else
-template <int N> constexpr int min_blocks() { return N <= 5 ? 6 : N <= 6 ? 5 : N <= 14 ? 4 : 3; }
+template <int N> constexpr int min_blocks() { return N <= 8 ? 6 : N <= 10 ? 5 : N <= 14 ? 4 : 3; }
 #endif
 
 // Carried filter state: [0, 2N) moments, [2N, 4N) what the next prediction starts from, mean, scale, nell, flag.

@@ -10,7 +10,7 @@ from mfs_b200.simulate import simulate_1d
 
 tag = sys.argv[1]
 for N in [int(a) for a in sys.argv[2:]]:
-    B, T = 227328, 100
+    B, T = (909312 if N <= 4 else 454656 if N <= 8 else 227328), 100
     dt, _, _, ic, drift, disp, _, pmf, _ = benes_bernoulli(N)
     fam = sde_cond_moments_tme(drift, disp, dt, 3)
     ys = simulate_1d(drift, disp, dt, T, ic, pmf, B, 100 + N, scheme='benes_exact')[2]
